@@ -1,0 +1,652 @@
+/*
+ * radix.cu -- LSD radix sort as a ONESWEEP: one histogram pass over the keys,
+ * then one pass per 8-bit digit that ranks, looks back and scatters in a single
+ * kernel.  Replaces the reference's per-digit {localsort, histogram, scan,
+ * scatter} sequence (/root/reference/src/cl_ops/sort/clo_sort_satradix.cl:34-258,
+ * host loop clo_sort_satradix.c:264-313) while keeping its result: a stable
+ * ascending sort on the raw key bits.
+ *
+ * Per pass a CTA
+ *   1. takes a tile ticket (tiles are handed out in launch order, which keeps the
+ *      look-back deadlock free and the sort stable),
+ *   2. loads TILE keys warp-striped (coalesced 128 B per warp instruction),
+ *   3. ranks every key inside its warp with ballot-built digit-match masks and a
+ *      warp-private shared-memory histogram (no atomics),
+ *   4. turns the warp histograms into tile-local digit offsets and publishes the
+ *      tile's 256 digit counts; decoupled look-back over the predecessor tiles
+ *      gives each digit's global offset (no global scan kernel),
+ *   5. stages the tile in shared memory in digit order and writes it out so that
+ *      consecutive threads write consecutive addresses within each digit run.
+ *
+ * HBM traffic (u32 keys): 4 B/key for the histogram + 4 passes x 8 B/key = 36 B/key.
+ */
+#include "clo_internal.h"
+#include "device_utils.cuh"
+#include "sort_common.h"
+
+#include <type_traits>
+
+using namespace clo;
+
+namespace {
+
+const int RADIX_BITS = 8;
+const int RADIX = 1 << RADIX_BITS;
+const int MAX_PASSES = 8;
+const unsigned SPIN_LIMIT = 1u << 26;
+
+struct PassCfg {
+	int passes;
+	u32 start_bit[MAX_PASSES];
+	u32 dmask[MAX_PASSES];
+};
+
+/* look-back word: 2 flag bits on top of the value */
+template <typename LbT> struct Lb;
+template <> struct Lb<u32> {
+	static constexpr u32 AGG = 1u << 30, PREFIX = 2u << 30, VAL = (1u << 30) - 1, FLAGS = 3u << 30;
+};
+template <> struct Lb<u64> {
+	static constexpr u64 AGG = 1ull << 62, PREFIX = 2ull << 62, VAL = (1ull << 62) - 1, FLAGS = 3ull << 62;
+};
+
+/* raw element -> (promoted) key bits the digits are cut from */
+template <typename ElemT, bool IDENTITY>
+__device__ __forceinline__ u64 radix_key(ElemT e, const CloKeySpec& ks) {
+	if (IDENTITY) return (u64) e;
+	u64 k = clo_extract_key((u64) e, ks);
+	/* OpenCL C promotes a sub-int signed key to int before `>>`
+	 * (clo_sort_satradix.cl:61): sign-extend to 32 bits */
+	if (ks.key_kind == CLO_KIND_SIGNED && ks.key_bits < 32) {
+		if (k & (1ull << (ks.key_bits - 1))) k |= (0xffffffffull & ~((1ull << ks.key_bits) - 1));
+	}
+	return k;
+}
+
+template <typename ElemT, bool IDENTITY>
+__device__ __forceinline__ u32 radix_digit(ElemT e, const CloKeySpec& ks, u32 start_bit, u32 dmask) {
+	if (IDENTITY) {
+		if (sizeof(ElemT) <= 4) return (((u32) e) >> start_bit) & dmask;
+		return (u32) (((u64) e) >> start_bit) & dmask;
+	}
+	return (u32) (radix_key<ElemT, false>(e, ks) >> start_bit) & dmask;
+}
+
+/* ------------------------------------------------------------- histogram */
+
+template <typename ElemT, bool IDENTITY, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+clo_radix_histogram(const ElemT* __restrict__ in, size_t n, u64* __restrict__ ghist,
+		PassCfg cfg, CloKeySpec ks, int vec_ok) {
+	__shared__ u32 sh[MAX_PASSES * RADIX];
+	for (int i = threadIdx.x; i < cfg.passes * RADIX; i += THREADS) sh[i] = 0;
+	__syncthreads();
+	constexpr int EPV = 16 / sizeof(ElemT);
+	const size_t stride = (size_t) gridDim.x * THREADS;
+	const size_t tid = (size_t) blockIdx.x * THREADS + threadIdx.x;
+	if (vec_ok) {
+		const size_t nvec = n / EPV;
+		for (size_t i = tid; i < nvec; i += stride) {
+			ElemT e[EPV];
+			load_vec_cs<ElemT, EPV>(in + i * EPV, e);
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) {
+				const u64 k = radix_key<ElemT, IDENTITY>(e[c], ks);
+				for (int p = 0; p < cfg.passes; ++p)
+					atomicAdd(&sh[p * RADIX + ((u32) (k >> cfg.start_bit[p]) & cfg.dmask[p])], 1u);
+			}
+		}
+		for (size_t i = nvec * EPV + tid; i < n; i += stride) {
+			const u64 k = radix_key<ElemT, IDENTITY>(in[i], ks);
+			for (int p = 0; p < cfg.passes; ++p)
+				atomicAdd(&sh[p * RADIX + ((u32) (k >> cfg.start_bit[p]) & cfg.dmask[p])], 1u);
+		}
+	} else {
+		for (size_t i = tid; i < n; i += stride) {
+			const u64 k = radix_key<ElemT, IDENTITY>(in[i], ks);
+			for (int p = 0; p < cfg.passes; ++p)
+				atomicAdd(&sh[p * RADIX + ((u32) (k >> cfg.start_bit[p]) & cfg.dmask[p])], 1u);
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < cfg.passes * RADIX; i += THREADS) {
+		const u32 c = sh[i];
+		if (c) atomicAdd(&ghist[i], (u64) c);
+	}
+}
+
+/* exclusive scan of each pass's 256 bins: block p handles pass p */
+__global__ void __launch_bounds__(RADIX)
+clo_radix_scan_bins(const u64* __restrict__ ghist, u64* __restrict__ bins_base) {
+	__shared__ u64 s_w[RADIX / 32];
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	const u64 c = ghist[blockIdx.x * RADIX + t];
+	const u64 incl = warp_inclusive_scan<u64>(c, lane);
+	if (lane == 31) s_w[warp] = incl;
+	__syncthreads();
+	u64 off = 0;
+	for (int w = 0; w < warp; ++w) off += s_w[w];
+	bins_base[blockIdx.x * RADIX + t] = off + incl - c;
+}
+
+/* -------------------------------------------------------------- onesweep */
+
+/* lanes of the warp whose digit equals mine (8 ballots) */
+__device__ __forceinline__ u32 match_digit_ballot(u32 d) {
+	u32 peers = 0xffffffffu;
+#pragma unroll
+	for (int b = 0; b < RADIX_BITS; ++b) {
+		const bool bit = (d >> b) & 1u;
+		const u32 m = __ballot_sync(0xffffffffu, bit);
+		peers &= bit ? m : ~m;
+	}
+	return peers;
+}
+
+template <int MATCH_HW>
+__device__ __forceinline__ u32 match_digit(u32 d) {
+	if (MATCH_HW) return __match_any_sync(0xffffffffu, d);
+	return match_digit_ballot(d);
+}
+
+/* A digit functor for the sample-sort partition: bucket = number of splitters
+ * (key, global index) that are <= (my key, my global index). */
+struct SplitterArgs {
+	const void* keys;       /* nparts-1 splitter keys, element type */
+	const u64* idx;         /* nparts-1 splitter global indices */
+	u32 count;              /* nparts-1 */
+	u64 gidx0;              /* global index of element 0 */
+};
+
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, bool PARTITION, typename LbT,
+	int THREADS, int IPT, int MATCH_HW>
+__global__ void __launch_bounds__(THREADS)
+clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
+		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
+		LbT* __restrict__ lookback, u32* __restrict__ ticket, const u64* __restrict__ bins_base,
+		u32 start_bit, u32 dmask, CloKeySpec ks, SplitterArgs sp, int* __restrict__ err_flag) {
+	constexpr int WARPS = THREADS / 32;
+	constexpr int TILE = THREADS * IPT;
+	static_assert(THREADS >= RADIX, "one thread per digit is needed");
+
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	u32* whist = reinterpret_cast<u32*>(smem_raw);                         /* [WARPS][RADIX] */
+	u32* s_dstart = whist + WARPS * RADIX;                                 /* [RADIX] */
+	u64* s_goff = reinterpret_cast<u64*>(s_dstart + RADIX);                /* [RADIX] */
+	u32* s_misc = reinterpret_cast<u32*>(s_goff + RADIX);                  /* [16]: tile, warp sums */
+	ElemT* skeys = reinterpret_cast<ElemT*>(s_misc + 16);                  /* [TILE] */
+	u32* svals = reinterpret_cast<u32*>(skeys + TILE);                     /* [TILE] if HAS_VAL */
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+	if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
+	for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+	__syncthreads();
+	const u32 tile = s_misc[0];
+	const size_t tile_base = (size_t) tile * TILE;
+	const bool full = tile_base + TILE <= n;
+	const u32 tile_count = full ? (u32) TILE : (u32) (n - tile_base);
+
+	/* ---- load, warp-striped: item i of lane l is element warp*32*IPT + i*32 + l */
+	ElemT key[IPT];
+	u32 val[HAS_VAL ? IPT : 1];
+	u32 pos[IPT];
+	const u32 wbase = (u32) warp * 32u * IPT + lane;
+#pragma unroll
+	for (int i = 0; i < IPT; ++i) {
+		const u32 local = wbase + i * 32u;
+		if (full || local < tile_count) {
+			key[i] = __ldcs(in + tile_base + local);
+			if (HAS_VAL) val[i] = __ldcs(vin + tile_base + local);
+		} else {
+			key[i] = ElemT(0);
+			if (HAS_VAL) val[i] = 0;
+		}
+	}
+
+	/* splitter table for the partition variant (tiny: <= 15 entries) */
+	ElemT sp_key[PARTITION ? 15 : 1];
+	u64 sp_idx[PARTITION ? 15 : 1];
+	if (PARTITION) {
+#pragma unroll
+		for (int s = 0; s < 15; ++s) {
+			if (s < (int) sp.count) {
+				sp_key[s] = reinterpret_cast<const ElemT*>(sp.keys)[s];
+				sp_idx[s] = sp.idx[s];
+			} else { sp_key[s] = ElemT(0); sp_idx[s] = 0; }
+		}
+	}
+
+	auto digit_of = [&](ElemT k, u32 local) -> u32 {
+		if (PARTITION) {
+			const u64 g = sp.gidx0 + tile_base + local;
+			u32 b = 0;
+#pragma unroll
+			for (int s = 0; s < 15; ++s)
+				if (s < (int) sp.count && (sp_key[s] < k || (sp_key[s] == k && sp_idx[s] <= g))) ++b;
+			return b;
+		}
+		return radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
+	};
+
+	/* ---- rank inside the warp */
+	u32* wh = whist + warp * RADIX;
+#pragma unroll
+	for (int i = 0; i < IPT; ++i) {
+		const u32 local = wbase + i * 32u;
+		const bool valid = full || local < tile_count;
+		const u32 d = digit_of(key[i], local);
+		u32 peers = match_digit<MATCH_HW>(d);
+		if (!full) peers &= __ballot_sync(0xffffffffu, valid);
+		const u32 lt = peers & lanemask_lt();
+		u32 old = 0;
+		if (valid && lt == 0) {            /* first lane of its digit group */
+			old = wh[d];
+			wh[d] = old + __popc(peers);
+		}
+		__syncwarp();
+		const int leader = __ffs(peers) - 1;
+		old = __shfl_sync(0xffffffffu, old, leader & 31);
+		pos[i] = old + __popc(lt);
+	}
+	__syncthreads();
+
+	/* ---- per digit (thread d): warp offsets, tile count, look-back */
+	u32 count = 0;
+	if (tid < RADIX) {
+#pragma unroll
+		for (int w = 0; w < WARPS; ++w) {
+			const u32 c = whist[w * RADIX + tid];
+			whist[w * RADIX + tid] = count;
+			count += c;
+		}
+	}
+	/* publish the tile aggregate as early as possible */
+	LbT* lb_mine = lookback + (size_t) tile * RADIX;
+	if (tid < RADIX) {
+		if (tile == 0) st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | (LbT) count));
+		else st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::AGG | (LbT) count));
+	}
+	/* exclusive scan of the 256 counts -> start of each digit inside the tile */
+	{
+		u32 incl = warp_inclusive_scan<u32>(count, lane);
+		if (tid < RADIX && lane == 31) s_misc[1 + warp] = incl;
+		__syncthreads();
+		if (tid < RADIX) {
+			u32 off = 0;
+#pragma unroll
+			for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[1 + w];
+			s_dstart[tid] = off + incl - count;
+		}
+	}
+	if (tid < RADIX) {
+		LbT excl = 0;
+		if (tile > 0) {
+			long long p = (long long) tile - 1;
+			unsigned spins = 0;
+			for (;;) {
+				const LbT w = ld_relaxed(lookback + (size_t) p * RADIX + tid);
+				const LbT f = w & Lb<LbT>::FLAGS;
+				if (f == 0) {
+					if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
+					continue;
+				}
+				excl += w & Lb<LbT>::VAL;
+				if (f == Lb<LbT>::PREFIX) break;
+				--p;
+			}
+			st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | ((excl + count) & Lb<LbT>::VAL)));
+		}
+		s_goff[tid] = bins_base[tid] + (u64) excl - (u64) s_dstart[tid];
+	}
+	__syncthreads();
+
+	/* ---- stage the tile in digit order */
+#pragma unroll
+	for (int i = 0; i < IPT; ++i) {
+		const u32 local = wbase + i * 32u;
+		if (full || local < tile_count) {
+			const u32 d = digit_of(key[i], local);
+			const u32 p = s_dstart[d] + wh[d] + pos[i];
+			skeys[p] = key[i];
+			if (HAS_VAL) svals[p] = val[i];
+			if (PARTITION) pos[i] = p;
+		}
+	}
+	__syncthreads();
+
+	/* ---- write out: thread j of the staged tile -> goff[digit] + j */
+	if (!PARTITION) {
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			const u32 j = (u32) tid + i * THREADS;
+			if (full || j < tile_count) {
+				const ElemT k = skeys[j];
+				const u32 d = radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
+				const u64 o = s_goff[d] + j;
+				out[o] = k;
+				if (HAS_VAL) vout[o] = svals[j];
+			}
+		}
+	} else {
+		/* the bucket of a staged element is not recomputable from the key alone
+		 * (ties are broken by global index): find it from the digit starts */
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			const u32 j = (u32) tid + i * THREADS;
+			if (full || j < tile_count) {
+				u32 d = 0;
+#pragma unroll
+				for (int s = 1; s < 16; ++s) if (s <= (int) sp.count && j >= s_dstart[s]) d = s;
+				const u64 o = s_goff[d] + j;
+				out[o] = skeys[j];
+				if (HAS_VAL) vout[o] = svals[j];
+			}
+		}
+	}
+}
+
+/* ------------------------------------------------------------- host side */
+
+template <typename ElemT, bool HAS_VAL> struct TileCfg {
+	/* keys-only: 512 x 16 (4 B and narrower), 512 x 8 (8 B); with payload: 512 x 12 / 512 x 8 */
+	static const int THREADS = 512;
+	static const int IPT = HAS_VAL ? (sizeof(ElemT) == 8 ? 8 : 12) : (sizeof(ElemT) == 8 ? 8 : 16);
+};
+
+template <typename ElemT, bool HAS_VAL, int THREADS, int IPT>
+constexpr size_t onesweep_smem() {
+	return (size_t) (THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8 + 16 * 4 +
+		(size_t) THREADS * IPT * sizeof(ElemT) + (HAS_VAL ? (size_t) THREADS * IPT * 4 : 0);
+}
+
+} // namespace
+
+struct CloRadixState {
+	CloScratch aux_keys;     /* ping-pong partner of the key buffer */
+	CloScratch aux_vals;
+	CloScratch work;         /* [err | ghist | bins_base | tickets | lookback...] */
+	int match_hw = 0;
+};
+
+CloRadixState* clo_radix_state_new() {
+	CloRadixState* st = new CloRadixState();
+	const char* e = getenv("CLO_RADIX_MATCH_HW");
+	st->match_hw = (e && *e == '1') ? 1 : 0;
+	return st;
+}
+
+void clo_radix_state_free(CloRadixState* st) {
+	if (!st) return;
+	st->aux_keys.release(); st->aux_vals.release(); st->work.release();
+	delete st;
+}
+
+int clo_radix_status(CloRadixState* st, cudaStream_t stream) {
+	if (!st || !st->work.ptr) return 0;
+	int flag = 0;
+	if (cudaMemcpyAsync(&flag, st->work.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return -1;
+	if (cudaStreamSynchronize(stream) != cudaSuccess) return -1;
+	return flag;
+}
+
+namespace {
+
+const size_t WORK_HDR = 256;                              /* err flag lives here */
+const size_t GHIST_BYTES = MAX_PASSES * RADIX * sizeof(u64);
+const size_t TICKET_BYTES = 256;
+
+struct WorkLayout {
+	int* err; u64* ghist; u64* bins; u32* tickets; void* lookback; size_t zero_bytes;
+};
+
+cudaError_t prepare_work(CloRadixState* st, size_t tiles, int passes, size_t lb_word, WorkLayout& L, cudaStream_t stream) {
+	const size_t lb_bytes = tiles * RADIX * lb_word * (size_t) passes;
+	const size_t total = WORK_HDR + GHIST_BYTES + GHIST_BYTES + TICKET_BYTES + lb_bytes;
+	cudaError_t e = st->work.reserve(total + total / 8);
+	if (e != cudaSuccess) return e;
+	char* base = (char*) st->work.ptr;
+	L.err = (int*) base;
+	L.ghist = (u64*) (base + WORK_HDR);
+	L.tickets = (u32*) (base + WORK_HDR + GHIST_BYTES);
+	L.lookback = base + WORK_HDR + GHIST_BYTES + TICKET_BYTES;
+	L.bins = (u64*) ((char*) L.lookback + lb_bytes);
+	/* everything up to the end of the look-back words is zeroed each call */
+	L.zero_bytes = WORK_HDR + GHIST_BYTES + TICKET_BYTES + lb_bytes;
+	return cudaMemsetAsync(base, 0, L.zero_bytes, stream);
+}
+
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int MATCH_HW>
+cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n,
+		LbT* lookback, u32* ticket, const u64* bins, u32 start_bit, u32 dmask, const CloKeySpec& ks,
+		int* err, cudaStream_t stream) {
+	constexpr int THREADS = TileCfg<ElemT, HAS_VAL>::THREADS;
+	constexpr int IPT = TileCfg<ElemT, HAS_VAL>::IPT;
+	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT>();
+	auto kern = clo_radix_onesweep<ElemT, HAS_VAL, IDENTITY, false, LbT, THREADS, IPT, MATCH_HW>;
+	static bool configured[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64 || !configured[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM);
+		if (e != cudaSuccess) return e;
+		if (dev >= 0 && dev < 64) configured[dev] = true;
+	}
+	const size_t tiles = (n + (size_t) THREADS * IPT - 1) / ((size_t) THREADS * IPT);
+	SplitterArgs sp = { nullptr, nullptr, 0, 0 };
+	kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, lookback, ticket, bins,
+		start_bit, dmask, ks, sp, err);
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
+}
+
+template <typename ElemT, bool HAS_VAL, bool IDENTITY>
+cudaError_t radix_sort_typed(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
+		const ElemT* src, ElemT* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
+	constexpr int THREADS = TileCfg<ElemT, HAS_VAL>::THREADS;
+	constexpr int IPT = TileCfg<ElemT, HAS_VAL>::IPT;
+	constexpr size_t TILE = (size_t) THREADS * IPT;
+	cudaError_t e;
+	PassCfg cfg;
+	cfg.passes = (int) ((sorted_bits + RADIX_BITS - 1) / RADIX_BITS);
+	for (int p = 0; p < MAX_PASSES; ++p) { cfg.start_bit[p] = 0; cfg.dmask[p] = 0; }
+	for (int p = 0; p < cfg.passes; ++p) {
+		const u32 rem = sorted_bits - (u32) p * RADIX_BITS;
+		cfg.start_bit[p] = (u32) p * RADIX_BITS;
+		cfg.dmask[p] = (1u << (rem < (u32) RADIX_BITS ? rem : (u32) RADIX_BITS)) - 1;
+	}
+	const size_t tiles = (n + TILE - 1) / TILE;
+	const bool wide = n >= (1ull << 30);
+	WorkLayout L;
+	if ((e = prepare_work(st, tiles, cfg.passes, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
+	if ((e = st->aux_keys.reserve(n * sizeof(ElemT))) != cudaSuccess) return e;
+	if (HAS_VAL && (e = st->aux_vals.reserve(n * sizeof(u32))) != cudaSuccess) return e;
+	ElemT* aux = (ElemT*) st->aux_keys.ptr;
+	u32* vaux = (u32*) st->aux_vals.ptr;
+
+	/* histogram of every digit in one read of the keys */
+	{
+		const int vec_ok = (reinterpret_cast<uintptr_t>(src) % 16) == 0;
+		size_t want = (n + 256 * 16 - 1) / (256 * 16);
+		size_t cap = (size_t) sm_count * 8;
+		const unsigned blocks = (unsigned) (want < cap ? (want ? want : 1) : cap);
+		clo_radix_histogram<ElemT, IDENTITY, 256><<<blocks, 256, 0, stream>>>(src, n, L.ghist, cfg, ks, vec_ok);
+		clo_radix_scan_bins<<<cfg.passes, RADIX, 0, stream>>>(L.ghist, L.bins);
+		CLO_COUNT_LAUNCH(2);
+		if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	}
+
+	/* ping-pong chain that ends in dst without touching src (unless in place):
+	 * odd number of passes: src->dst->aux->dst...; even: src->aux->dst->aux->dst */
+	const ElemT* cur = src; const u32* vcur = vsrc;
+	if ((const void*) src == (const void*) dst && (cfg.passes & 1)) {
+		/* in place with an odd number of passes: start the chain from the aux copy */
+		if ((e = cudaMemcpyAsync(aux, src, n * sizeof(ElemT), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+		cur = aux;
+		if (HAS_VAL) {
+			if ((e = cudaMemcpyAsync(vaux, vsrc, n * sizeof(u32), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+			vcur = vaux;
+		}
+	}
+	for (int p = 0; p < cfg.passes; ++p) {
+		const bool to_dst = ((cfg.passes - 1 - p) % 2) == 0;
+		ElemT* nxt = to_dst ? dst : aux;
+		u32* vnxt = to_dst ? vdst : vaux;
+		u32* ticket = L.tickets + p;
+		if (wide) {
+			u64* lb = (u64*) L.lookback + (size_t) p * tiles * RADIX;
+			e = st->match_hw
+				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 1>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
+				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+		} else {
+			u32* lb = (u32*) L.lookback + (size_t) p * tiles * RADIX;
+			e = st->match_hw
+				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 1>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
+				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+		}
+		if (e != cudaSuccess) return e;
+		cur = nxt; vcur = vnxt;
+	}
+	return cudaSuccess;
+}
+
+template <typename ElemT>
+cudaError_t radix_sort_elem(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
+		const void* src, void* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
+	const bool has_val = vsrc != nullptr;
+	if (has_val) {
+		if (ks.identity) return radix_sort_typed<ElemT, true, true>(st, sm_count, ks, sorted_bits, (const ElemT*) src, (ElemT*) dst, vsrc, vdst, n, stream);
+		return radix_sort_typed<ElemT, true, false>(st, sm_count, ks, sorted_bits, (const ElemT*) src, (ElemT*) dst, vsrc, vdst, n, stream);
+	}
+	if (ks.identity) return radix_sort_typed<ElemT, false, true>(st, sm_count, ks, sorted_bits, (const ElemT*) src, (ElemT*) dst, vsrc, vdst, n, stream);
+	return radix_sort_typed<ElemT, false, false>(st, sm_count, ks, sorted_bits, (const ElemT*) src, (ElemT*) dst, vsrc, vdst, n, stream);
+}
+
+} // namespace
+
+cudaError_t clo_radix_sort(CloRadixState* st, int sm_count, size_t elem_size, const CloKeySpec& ks,
+		uint32_t sorted_bits, const void* src, void* dst, const uint32_t* payload_src, uint32_t* payload_dst,
+		size_t n, cudaStream_t stream, const char** err_msg) {
+	if (n == 0) return cudaSuccess;
+	if (n >= (1ull << 40)) { if (err_msg) *err_msg = "radix sort: too many elements"; return cudaErrorInvalidValue; }
+	if (sorted_bits == 0 || sorted_bits > 64) { if (err_msg) *err_msg = "radix sort: invalid number of key bits"; return cudaErrorInvalidValue; }
+	if (payload_src && elem_size < 4) { if (err_msg) *err_msg = "radix sort: payload needs 4- or 8-byte keys"; return cudaErrorInvalidValue; }
+	switch (elem_size) {
+	case 1: return radix_sort_elem<unsigned char>(st, sm_count, ks, sorted_bits, src, dst, nullptr, nullptr, n, stream);
+	case 2: return radix_sort_elem<unsigned short>(st, sm_count, ks, sorted_bits, src, dst, nullptr, nullptr, n, stream);
+	case 4: return radix_sort_elem<u32>(st, sm_count, ks, sorted_bits, src, dst, payload_src, payload_dst, n, stream);
+	case 8: return radix_sort_elem<u64>(st, sm_count, ks, sorted_bits, src, dst, payload_src, payload_dst, n, stream);
+	default: if (err_msg) *err_msg = "radix sort: unsupported element size"; return cudaErrorInvalidValue;
+	}
+}
+
+/* ------------------------------------------------------------- partition */
+
+namespace {
+
+template <typename ElemT, bool HAS_VAL>
+cudaError_t partition_typed(CloRadixState* st, const ElemT* in, const u32* vin, ElemT* out, u32* vout, size_t n,
+		u64 gidx0, const void* sk, const u64* si, u32 nparts, u64* counts_out, cudaStream_t stream);
+
+/* bucket histogram: counts per bucket (same bucket function as the onesweep variant) */
+template <typename ElemT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+clo_partition_histogram(const ElemT* __restrict__ in, size_t n, SplitterArgs sp, u64* __restrict__ ghist) {
+	__shared__ u32 sh[16];
+	__shared__ ElemT s_key[15];
+	__shared__ u64 s_idx[15];
+	if (threadIdx.x < 16) sh[threadIdx.x] = 0;
+	if (threadIdx.x < sp.count) {
+		s_key[threadIdx.x] = reinterpret_cast<const ElemT*>(sp.keys)[threadIdx.x];
+		s_idx[threadIdx.x] = sp.idx[threadIdx.x];
+	}
+	__syncthreads();
+	u32 local[16];
+#pragma unroll
+	for (int b = 0; b < 16; ++b) local[b] = 0;
+	for (size_t i = (size_t) blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t) gridDim.x * THREADS) {
+		const ElemT k = __ldcs(in + i);
+		const u64 g = sp.gidx0 + i;
+		u32 b = 0;
+		for (u32 s = 0; s < sp.count; ++s)
+			if (s_key[s] < k || (s_key[s] == k && s_idx[s] <= g)) ++b;
+#pragma unroll
+		for (int q = 0; q < 16; ++q) if (q == (int) b) local[q]++;
+	}
+#pragma unroll
+	for (int b = 0; b < 16; ++b) {
+		const u32 t = warp_reduce_sum<u32>(local[b]);
+		if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sh[b], t);
+	}
+	__syncthreads();
+	if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], (u64) sh[threadIdx.x]);
+}
+
+/* bins_base[b] = exclusive scan of the bucket counts; counts_out[b] = count */
+__global__ void clo_partition_scan_bins(const u64* __restrict__ ghist, u64* __restrict__ bins_base,
+		u64* __restrict__ counts_out, u32 nparts) {
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		u64 run = 0;
+		for (u32 b = 0; b < (u32) RADIX; ++b) {
+			const u64 c = b < 16 ? ghist[b] : 0;
+			bins_base[b] = run;
+			run += c;
+			if (b < nparts && counts_out) counts_out[b] = c;
+		}
+	}
+}
+
+template <typename ElemT, bool HAS_VAL>
+cudaError_t partition_typed(CloRadixState* st, const ElemT* in, const u32* vin, ElemT* out, u32* vout, size_t n,
+		u64 gidx0, const void* sk, const u64* si, u32 nparts, u64* counts_out, cudaStream_t stream) {
+	constexpr int THREADS = TileCfg<ElemT, HAS_VAL>::THREADS;
+	constexpr int IPT = TileCfg<ElemT, HAS_VAL>::IPT;
+	constexpr size_t TILE = (size_t) THREADS * IPT;
+	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT>();
+	const size_t tiles = (n + TILE - 1) / TILE;
+	const bool wide = n >= (1ull << 30);
+	WorkLayout L;
+	cudaError_t e;
+	if ((e = prepare_work(st, tiles, 1, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
+	SplitterArgs sp = { sk, si, nparts - 1, gidx0 };
+	CloKeySpec ks = {};
+	ks.identity = 1;
+	const unsigned hb = (unsigned) (tiles < 1184 ? (tiles ? tiles : 1) : 1184);
+	clo_partition_histogram<ElemT, 256><<<hb, 256, 0, stream>>>(in, n, sp, L.ghist);
+	clo_partition_scan_bins<<<1, 32, 0, stream>>>(L.ghist, L.bins, counts_out, nparts);
+	CLO_COUNT_LAUNCH(2);
+	if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	if (n == 0) return cudaSuccess;
+	if (wide) {
+		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u64, THREADS, IPT, 0>;
+		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
+		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u64*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err);
+	} else {
+		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u32, THREADS, IPT, 0>;
+		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
+		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u32*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err);
+	}
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
+}
+
+} // namespace
+
+cudaError_t clo_radix_partition(CloRadixState* st, size_t elem_size, const void* keys_in,
+		const uint32_t* payload_in, void* keys_out, uint32_t* payload_out, size_t n, uint64_t gidx0,
+		const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out,
+		cudaStream_t stream, const char** err_msg) {
+	if (nparts < 1 || nparts > 16) { if (err_msg) *err_msg = "partition: nparts must be in [1,16]"; return cudaErrorInvalidValue; }
+	if (n >= (1ull << 40)) { if (err_msg) *err_msg = "partition: too many elements"; return cudaErrorInvalidValue; }
+	const bool has_val = payload_in != nullptr;
+	if (elem_size == 4) {
+		if (has_val) return partition_typed<u32, true>(st, (const u32*) keys_in, payload_in, (u32*) keys_out, payload_out, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
+		return partition_typed<u32, false>(st, (const u32*) keys_in, nullptr, (u32*) keys_out, nullptr, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
+	}
+	if (elem_size == 8) {
+		if (has_val) return partition_typed<u64, true>(st, (const u64*) keys_in, payload_in, (u64*) keys_out, payload_out, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
+		return partition_typed<u64, false>(st, (const u64*) keys_in, nullptr, (u64*) keys_out, nullptr, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
+	}
+	if (err_msg) *err_msg = "partition: keys must be 4 or 8 bytes";
+	return cudaErrorInvalidValue;
+}

@@ -1,0 +1,626 @@
+/*
+ * scan.cu -- clo_scan: exclusive prefix sum as ONE single-pass decoupled
+ * look-back kernel (replaces the reference's three Blelloch kernels,
+ * /root/reference/src/cl_ops/scan/clo_scan_blelloch.cl:49-211 and the host loop
+ * clo_scan_blelloch.c:78-214; API object: clo_scan_abstract.c:74-567).
+ *
+ * Semantics kept: out[0] = 0, out[i] = sum_{j<i} (SUM)in[j], SUM-type arithmetic
+ * (integer wrap-around; float sums carry the inter-tile prefix in f64).
+ *
+ * HBM traffic: numel * (sizeof(elem) + sizeof(sum)) bytes, read once, written once.
+ */
+#include "clo_internal.h"
+#include "device_utils.cuh"
+
+#include <cstring>
+#include <type_traits>
+
+using namespace clo;
+
+namespace {
+
+/* ------------------------------------------------------------------ traits */
+
+template <typename SumT> struct AccOf {
+	typedef typename std::conditional<std::is_floating_point<SumT>::value, double,
+		typename std::conditional<sizeof(SumT) == 8, u64, u32>::type>::type type;
+};
+
+template <typename AccT> struct AccWords;
+template <> struct AccWords<u32> {
+	static const int N = 1;
+	__device__ static void pack(u32 v, u32 (&w)[1]) { w[0] = v; }
+	__device__ static u32 unpack(const u32 (&w)[1]) { return w[0]; }
+};
+template <> struct AccWords<u64> {
+	static const int N = 2;
+	__device__ static void pack(u64 v, u32 (&w)[2]) { w[0] = (u32) v; w[1] = (u32) (v >> 32); }
+	__device__ static u64 unpack(const u32 (&w)[2]) { return (u64) w[0] | ((u64) w[1] << 32); }
+};
+template <> struct AccWords<double> {
+	static const int N = 2;
+	__device__ static void pack(double v, u32 (&w)[2]) {
+		u64 b = (u64) __double_as_longlong(v); w[0] = (u32) b; w[1] = (u32) (b >> 32);
+	}
+	__device__ static double unpack(const u32 (&w)[2]) {
+		return __longlong_as_double((long long) ((u64) w[0] | ((u64) w[1] << 32)));
+	}
+};
+
+/* (SUM) in[j], widened to the accumulator: clo_scan_blelloch.cl:79-80 */
+template <typename ElemT, typename SumT, typename AccT>
+__device__ __forceinline__ AccT to_acc(ElemT e) {
+	return static_cast<AccT>(static_cast<SumT>(e));
+}
+
+enum { ST_AGG = 1, ST_PREFIX = 2 };
+const unsigned SPIN_LIMIT = 1u << 26;
+
+/* ------------------------------------------------------------------ kernel */
+
+template <typename ElemT, typename SumT, int THREADS, int VPT>
+__global__ void __launch_bounds__(THREADS)
+clo_scan_lookback(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n,
+		u64* __restrict__ desc, u32* __restrict__ ticket, u32 ticket_base, u32 epoch,
+		const SumT* __restrict__ carry_in, int vec_in, int vec_out, int* __restrict__ err_flag) {
+	typedef typename AccOf<SumT>::type AccT;
+	typedef AccWords<AccT> AW;
+	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;       /* elements per vector */
+	constexpr int WARPS = THREADS / 32;
+	constexpr int TILE = THREADS * VPT * EPV;
+	/* output chunk: at most 16 bytes per store */
+	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
+
+	__shared__ u32 s_tile;
+	__shared__ AccT s_warp[WARPS];
+	__shared__ AccT s_prefix;
+
+	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
+	__syncthreads();
+	const u32 tile = s_tile;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const size_t tile_base = (size_t) tile * TILE;
+	const bool full = tile_base + TILE <= n;
+
+	/* ---- load: warp-striped vectors (row j of warp w is 32*EPV contiguous elements) */
+	AccT v[VPT][EPV];
+#pragma unroll
+	for (int j = 0; j < VPT; ++j) {
+		const size_t idx = tile_base + ((size_t) (warp * VPT + j) * 32 + lane) * EPV;
+		ElemT e[EPV];
+		if (vec_in && (full || idx + EPV <= n)) {
+			load_vec_cs<ElemT, EPV>(in + idx, e);
+		} else {
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) e[c] = (idx + c < n) ? in[idx + c] : ElemT(0);
+		}
+#pragma unroll
+		for (int c = 0; c < EPV; ++c) v[j][c] = to_acc<ElemT, SumT, AccT>(e[c]);
+	}
+
+	/* ---- thread: inclusive scan inside each vector; warp: scan of vector sums per row */
+	AccT base[VPT];
+	AccT warp_total = AccT(0);
+#pragma unroll
+	for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+		for (int c = 1; c < EPV; ++c) v[j][c] += v[j][c - 1];
+		AccT incl = warp_inclusive_scan<AccT>(v[j][EPV - 1], lane);
+		AccT excl = __shfl_up_sync(0xffffffffu, incl, 1);
+		if (lane == 0) excl = AccT(0);
+		AccT row_total = __shfl_sync(0xffffffffu, incl, 31);
+		base[j] = warp_total + excl;
+		warp_total += row_total;
+	}
+
+	/* ---- block: offsets of the warps, tile aggregate */
+	if (lane == 0) s_warp[warp] = warp_total;
+	__syncthreads();
+	AccT warp_off = AccT(0), aggregate = AccT(0);
+#pragma unroll
+	for (int w = 0; w < WARPS; ++w) {
+		AccT t = s_warp[w];
+		if (w < warp) warp_off += t;
+		aggregate += t;
+	}
+
+	/* ---- decoupled look-back (warp 0; lane i inspects tile-1-i) */
+	if (warp == 0) {
+		const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
+		const u64 fl_agg = ((u64) ((epoch << 2) | ST_AGG)) << 32;
+		const u64 fl_pre = ((u64) ((epoch << 2) | ST_PREFIX)) << 32;
+		u64* mine = desc + (size_t) tile * AW::N;
+		AccT exclusive = carry;
+		if (tile == 0) {
+			if (lane == 0) {
+				u32 w[AW::N];
+				AW::pack(carry + aggregate, w);
+#pragma unroll
+				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
+			}
+		} else {
+			if (lane == 0) {
+				u32 w[AW::N];
+				AW::pack(aggregate, w);
+#pragma unroll
+				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_agg | w[k]);
+			}
+			exclusive = AccT(0);
+			long long look = (long long) tile - 1;
+			unsigned spins = 0;
+			bool done = false;
+			while (!done) {
+				const long long idx = look - lane;
+				u32 state = ST_PREFIX;  /* lanes before tile 0 act as an empty prefix */
+				AccT val = AccT(0);
+				if (idx >= 0) {
+					const u64* p = desc + (size_t) idx * AW::N;
+					for (;;) {
+						u32 w[AW::N];
+						u32 st = 0;
+						bool ok = true;
+#pragma unroll
+						for (int k = 0; k < AW::N; ++k) {
+							const u64 x = ld_relaxed(p + k);
+							const u32 f = (u32) (x >> 32);
+							w[k] = (u32) x;
+							if ((f >> 2) != epoch || (f & 3u) == 0) ok = false;
+							if (k == 0) st = f & 3u; else if ((f & 3u) != st) ok = false;
+						}
+						if (ok) { state = st; val = AW::unpack(w); break; }
+						if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
+					}
+				} else if (idx == -1) {
+					val = carry;   /* the scan's carry-in sits "before tile 0" */
+				}
+				const u32 pmask = __ballot_sync(0xffffffffu, state == ST_PREFIX);
+				const int first = pmask ? (__ffs(pmask) - 1) : 32;
+				AccT contrib = (lane <= first) ? val : AccT(0);
+				exclusive += warp_reduce_sum<AccT>(contrib);
+				done = (pmask != 0);
+				look -= 32;
+			}
+			if (lane == 0) {
+				u32 w[AW::N];
+				AW::pack(exclusive + aggregate, w);
+#pragma unroll
+				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
+			}
+		}
+		if (lane == 0) s_prefix = exclusive;
+	}
+	__syncthreads();
+	const AccT tile_prefix = s_prefix + warp_off;
+
+	/* ---- store: same warp-striped layout */
+#pragma unroll
+	for (int j = 0; j < VPT; ++j) {
+		const size_t idx = tile_base + ((size_t) (warp * VPT + j) * 32 + lane) * EPV;
+		const AccT b = tile_prefix + base[j];
+		SumT o[EPV];
+		o[0] = static_cast<SumT>(b);
+#pragma unroll
+		for (int c = 1; c < EPV; ++c) o[c] = static_cast<SumT>(b + v[j][c - 1]);
+		if (vec_out && (full || idx + EPV <= n)) {
+#pragma unroll
+			for (int c0 = 0; c0 < EPV; c0 += OCH) {
+				SumT chunk[OCH];
+#pragma unroll
+				for (int c = 0; c < OCH; ++c) chunk[c] = o[c0 + c];
+				store_vec_cs<SumT, OCH>(out + idx + c0, chunk);
+			}
+		} else {
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) if (idx + c < n) out[idx + c] = o[c];
+		}
+	}
+}
+
+/* Two-phase deterministic reduction (multi-GPU scan: per-GPU total). */
+template <typename ElemT, typename SumT, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+clo_scan_reduce_partial(const ElemT* __restrict__ in, size_t n, typename AccOf<SumT>::type* __restrict__ partial) {
+	typedef typename AccOf<SumT>::type AccT;
+	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
+	__shared__ AccT s_warp[THREADS / 32];
+	AccT acc = AccT(0);
+	const size_t nvec = n / EPV;
+	const bool vec_ok = (reinterpret_cast<uintptr_t>(in) % (sizeof(ElemT) * EPV)) == 0;
+	if (vec_ok) {
+		for (size_t i = (size_t) blockIdx.x * THREADS + threadIdx.x; i < nvec; i += (size_t) gridDim.x * THREADS) {
+			ElemT e[EPV];
+			load_vec_cs<ElemT, EPV>(in + i * EPV, e);
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) acc += to_acc<ElemT, SumT, AccT>(e[c]);
+		}
+		for (size_t i = nvec * EPV + (size_t) blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t) gridDim.x * THREADS)
+			acc += to_acc<ElemT, SumT, AccT>(in[i]);
+	} else {
+		for (size_t i = (size_t) blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t) gridDim.x * THREADS)
+			acc += to_acc<ElemT, SumT, AccT>(in[i]);
+	}
+	acc = warp_reduce_sum<AccT>(acc);
+	if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		AccT t = AccT(0);
+		for (int w = 0; w < THREADS / 32; ++w) t += s_warp[w];
+		partial[blockIdx.x] = t;
+	}
+}
+
+template <typename SumT>
+__global__ void clo_scan_reduce_final(const typename AccOf<SumT>::type* __restrict__ partial, int count,
+		SumT* __restrict__ total_out) {
+	typedef typename AccOf<SumT>::type AccT;
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		AccT t = AccT(0);
+		for (int i = 0; i < count; ++i) t += partial[i];
+		*total_out = static_cast<SumT>(t);
+	}
+}
+
+/* --------------------------------------------------------------- host side */
+
+const int SCAN_THREADS = 256;
+const int SCAN_VPT = 4;
+
+struct ScanState {
+	CloScratch scratch;        /* [ticket(u32) | err(int) | pad | descriptors...] */
+	size_t tiles_cap = 0;
+	u32 epoch = 0;
+	u32 ticket_base = 0;
+	CloScratch partials;
+};
+
+const size_t HDR_BYTES = 256;
+
+template <typename ElemT, typename SumT>
+cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, const void* carry, cudaStream_t stream) {
+	typedef typename AccOf<SumT>::type AccT;
+	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
+	constexpr size_t TILE = (size_t) SCAN_THREADS * SCAN_VPT * EPV;
+	const size_t tiles = (n + TILE - 1) / TILE;
+	if (tiles >= 0xffffffffull) return cudaErrorInvalidValue;
+	cudaError_t e;
+	if (tiles > st.tiles_cap) {
+		/* descriptors are sized for the widest accumulator (2 words) */
+		size_t cap = tiles + tiles / 4 + 1024;
+		if ((e = st.scratch.reserve(HDR_BYTES + cap * 2 * sizeof(u64))) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(st.scratch.ptr, 0, st.scratch.size, stream)) != cudaSuccess) return e;
+		st.tiles_cap = cap; st.epoch = 0; st.ticket_base = 0;
+	}
+	if (st.epoch >= (1u << 30) - 2) {
+		if ((e = cudaMemsetAsync(st.scratch.ptr, 0, st.scratch.size, stream)) != cudaSuccess) return e;
+		st.epoch = 0; st.ticket_base = 0;
+	}
+	st.epoch += 1;
+	u32* ticket = (u32*) st.scratch.ptr;
+	int* err_flag = (int*) st.scratch.ptr + 1;
+	u64* desc = (u64*) ((char*) st.scratch.ptr + HDR_BYTES);
+	const int vec_in = (reinterpret_cast<uintptr_t>(in) % (sizeof(ElemT) * EPV)) == 0;
+	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
+	const int vec_out = (reinterpret_cast<uintptr_t>(out) % (sizeof(SumT) * OCH)) == 0;
+	clo_scan_lookback<ElemT, SumT, SCAN_THREADS, SCAN_VPT><<<(unsigned) tiles, SCAN_THREADS, 0, stream>>>(
+		(const ElemT*) in, (SumT*) out, n, desc, ticket, st.ticket_base, st.epoch,
+		(const SumT*) carry, vec_in, vec_out, err_flag);
+	CLO_COUNT_LAUNCH(1);
+	st.ticket_base += (u32) tiles;
+	(void) sizeof(AccT);
+	return cudaGetLastError();
+}
+
+template <typename ElemT, typename SumT>
+cudaError_t launch_reduce(ScanState& st, const void* in, void* total_out, size_t n, int sms, cudaStream_t stream) {
+	typedef typename AccOf<SumT>::type AccT;
+	const int blocks = sms * 8;
+	cudaError_t e;
+	if ((e = st.partials.reserve((size_t) blocks * sizeof(AccT))) != cudaSuccess) return e;
+	clo_scan_reduce_partial<ElemT, SumT, 256><<<blocks, 256, 0, stream>>>((const ElemT*) in, n, (AccT*) st.partials.ptr);
+	clo_scan_reduce_final<SumT><<<1, 32, 0, stream>>>((const AccT*) st.partials.ptr, blocks, (SumT*) total_out);
+	CLO_COUNT_LAUNCH(2);
+	return cudaGetLastError();
+}
+
+typedef cudaError_t (*ScanFn)(ScanState&, const void*, void*, size_t, const void*, cudaStream_t);
+typedef cudaError_t (*ReduceFn)(ScanState&, const void*, void*, size_t, int, cudaStream_t);
+
+/* CloType -> C++ type (half is not an arithmetic type in OpenCL C without
+ * cl_khr_fp16; unsupported here as well) */
+template <int T> struct CT;
+template <> struct CT<CLO_CHAR> { typedef signed char type; };
+template <> struct CT<CLO_UCHAR> { typedef unsigned char type; };
+template <> struct CT<CLO_SHORT> { typedef short type; };
+template <> struct CT<CLO_USHORT> { typedef unsigned short type; };
+template <> struct CT<CLO_INT> { typedef int type; };
+template <> struct CT<CLO_UINT> { typedef unsigned int type; };
+template <> struct CT<CLO_LONG> { typedef long long type; };
+template <> struct CT<CLO_ULONG> { typedef unsigned long long type; };
+template <> struct CT<CLO_FLOAT> { typedef float type; };
+template <> struct CT<CLO_DOUBLE> { typedef double type; };
+
+template <int E, int S> struct Entry {
+	static ScanFn scan() { return &launch_scan<typename CT<E>::type, typename CT<S>::type>; }
+	static ReduceFn reduce() { return &launch_reduce<typename CT<E>::type, typename CT<S>::type>; }
+};
+
+#define CLO_TYPE_CASES(M) \
+	M(CLO_CHAR) M(CLO_UCHAR) M(CLO_SHORT) M(CLO_USHORT) M(CLO_INT) M(CLO_UINT) \
+	M(CLO_LONG) M(CLO_ULONG) M(CLO_FLOAT) M(CLO_DOUBLE)
+
+template <int E> ScanFn scan_for_sum(int s) {
+	switch (s) {
+#define CLO_M(S) case S: return Entry<E, S>::scan();
+	CLO_TYPE_CASES(CLO_M)
+#undef CLO_M
+	default: return nullptr;
+	}
+}
+
+template <int E> ReduceFn reduce_for_sum(int s) {
+	switch (s) {
+#define CLO_M(S) case S: return Entry<E, S>::reduce();
+	CLO_TYPE_CASES(CLO_M)
+#undef CLO_M
+	default: return nullptr;
+	}
+}
+
+ScanFn find_scan(int e, int s) {
+	switch (e) {
+#define CLO_M(E) case E: return scan_for_sum<E>(s);
+	CLO_TYPE_CASES(CLO_M)
+#undef CLO_M
+	default: return nullptr;
+	}
+}
+
+ReduceFn find_reduce(int e, int s) {
+	switch (e) {
+#define CLO_M(E) case E: return reduce_for_sum<E>(s);
+	CLO_TYPE_CASES(CLO_M)
+#undef CLO_M
+	default: return nullptr;
+	}
+}
+
+} // namespace
+
+/* ------------------------------------------------------------------ object */
+
+struct clo_scan {
+	CloScanImplDef impl_def;
+	CCLContext* ctx;
+	CCLProgram* prg;
+	CloType elem_type;
+	CloType sum_type;
+	void* data;
+	/* backend state */
+	ScanState st;
+	ScanFn fn;
+	ReduceFn rfn;
+};
+
+static ccl_program g_scan_program = { "clo_scan (precompiled sm_100a)" };
+
+static const char* blelloch_init(CloScan* scanner, const char* options, GError** err) {
+	(void) scanner;
+	/* clo_scan_blelloch.c:43-45: no options are accepted */
+	if (options && *options) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Invalid options for blelloch scan.");
+		return NULL;
+	}
+	return "";
+}
+
+static void blelloch_finalize(CloScan* scanner) { (void) scanner; }
+
+static int scan_check_error_flag(CloScan* scanner, cudaStream_t stream, GError** err) {
+	if (!scanner->st.scratch.ptr) return 0;
+	int flag = 0;
+	if (clo_cuda_failed(cudaMemcpyAsync(&flag, (int*) scanner->st.scratch.ptr + 1, sizeof(int),
+			cudaMemcpyDeviceToHost, stream), err, "scan status read")) return 1;
+	if (clo_cuda_failed(cudaStreamSynchronize(stream), err, "scan sync")) return 1;
+	if (flag) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "scan look-back timed out (device status flag set)");
+		return 1;
+	}
+	return 0;
+}
+
+static CCLEvent* scan_device(CloScan* scanner, CCLQueue* cq_exec, CCLBuffer* data_in,
+		CCLBuffer* data_out, CCLBuffer* carry, size_t numel, GError** err) {
+	if (!scanner || !cq_exec || !data_in || !data_out) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "scan: NULL argument");
+		return NULL;
+	}
+	const size_t es = clo_type_sizeof(scanner->elem_type), ss = clo_type_sizeof(scanner->sum_type);
+	if (data_in->size < numel * es || data_out->size < numel * ss) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "scan: buffers too small for %zu elements", numel);
+		return NULL;
+	}
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_scan_lookback");
+	cudaError_t rc = cudaSuccess;
+	if (numel > 0)
+		rc = scanner->fn(scanner->st, data_in->ptr, data_out->ptr, numel, carry ? carry->ptr : NULL, cq_exec->stream);
+	clo_queue_end(cq_exec, evt);
+	if (clo_cuda_failed(rc, err, "clo_scan_lookback launch")) return NULL;
+	return evt;
+}
+
+static CCLEvent* blelloch_scan_with_device_data(CloScan* scanner, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		CCLBuffer* data_in, CCLBuffer* data_out, size_t numel, size_t lws_max, GError** err) {
+	(void) cq_comm; (void) lws_max;
+	return scan_device(scanner, cq_exec, data_in, data_out, NULL, numel, err);
+}
+
+static const char* const kScanKernels[] = { "clo_scan_lookback" };
+
+static cl_uint blelloch_get_num_kernels(CloScan* scanner, GError** err) { (void) scanner; (void) err; return 1; }
+
+static const char* blelloch_get_kernel_name(CloScan* scanner, cl_uint i, GError** err) {
+	(void) scanner;
+	if (i >= 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
+	return kScanKernels[i];
+}
+
+static size_t blelloch_get_localmem_usage(CloScan* scanner, cl_uint i, size_t lws_max, size_t numel, GError** err) {
+	(void) lws_max; (void) numel;
+	if (i >= 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
+	/* s_tile + per-warp totals + tile prefix */
+	const size_t acc = clo_type_sizeof(scanner->sum_type) == 8 || scanner->sum_type >= CLO_FLOAT ? 8 : 4;
+	return 8 + (SCAN_THREADS / 32 + 1) * acc;
+}
+
+extern "C" const CloScanImplDef clo_scan_blelloch_def = {
+	"blelloch", blelloch_init, blelloch_finalize, blelloch_scan_with_device_data,
+	blelloch_get_num_kernels, blelloch_get_kernel_name, blelloch_get_localmem_usage
+};
+
+extern "C" CloScan* clo_scan_new(const char* type, const char* options, CCLContext* ctx,
+		CloType elem_type, CloType sum_type, const char* compiler_opts, GError** err) {
+	(void) compiler_opts; /* OpenCL build options have no meaning here; accepted and ignored */
+	if (err && *err) return NULL;
+	if (!ctx) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "NULL context"); return NULL; }
+	if (!type || strcmp(type, clo_scan_blelloch_def.name) != 0) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_IMPL_NOT_FOUND,
+			"The requested scan implementation, '%s', was not found.", type ? type : "(null)");
+		return NULL;
+	}
+	ScanFn fn = find_scan((int) elem_type, (int) sum_type);
+	if (!fn) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_UNKNOWN_TYPE,
+			"Unsupported scan types (elem=%d, sum=%d)", (int) elem_type, (int) sum_type);
+		return NULL;
+	}
+	clo_scan* s = new clo_scan();
+	s->impl_def = clo_scan_blelloch_def;
+	s->ctx = ctx; ccl_context_ref(ctx);
+	s->prg = &g_scan_program;
+	s->elem_type = elem_type; s->sum_type = sum_type;
+	s->data = NULL;
+	s->fn = fn; s->rfn = find_reduce((int) elem_type, (int) sum_type);
+	GError* ierr = NULL;
+	s->impl_def.init(s, options, &ierr);
+	if (ierr) { g_propagate_error(err, ierr); clo_scan_destroy(s); return NULL; }
+	clo_handle_add(s);
+	return s;
+}
+
+extern "C" void clo_scan_destroy(CloScan* scan) {
+	if (!scan) return;
+	clo_handle_remove(scan);
+	scan->impl_def.finalize(scan);
+	{
+		CloDeviceGuard g(scan->ctx->dev.ordinal);
+		scan->st.scratch.release();
+		scan->st.partials.release();
+	}
+	ccl_context_unref(scan->ctx);
+	delete scan;
+}
+
+extern "C" CCLEvent* clo_scan_with_device_data(CloScan* scanner, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		CCLBuffer* data_in, CCLBuffer* data_out, size_t numel, size_t lws_max, GError** err) {
+	if (!scanner || (err && *err) || !cq_exec) return NULL;
+	return scanner->impl_def.scan_with_device_data(scanner, cq_exec, cq_comm, data_in, data_out, numel, lws_max, err);
+}
+
+extern "C" CCLEvent* clo_scan_with_device_data_carry(CloScan* scanner, CCLQueue* cq_exec,
+		CCLBuffer* data_in, CCLBuffer* data_out, CCLBuffer* carry_in, size_t numel, GError** err) {
+	if (!scanner || (err && *err) || !cq_exec) return NULL;
+	return scan_device(scanner, cq_exec, data_in, data_out, carry_in, numel, err);
+}
+
+extern "C" CCLEvent* clo_scan_reduce_with_device_data(CloScan* scanner, CCLQueue* cq_exec,
+		CCLBuffer* data_in, CCLBuffer* total_out, size_t numel, GError** err) {
+	if (!scanner || (err && *err) || !cq_exec || !data_in || !total_out) return NULL;
+	if (data_in->size < numel * clo_type_sizeof(scanner->elem_type) ||
+			total_out->size < clo_type_sizeof(scanner->sum_type)) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "scan reduce: buffers too small");
+		return NULL;
+	}
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_scan_reduce");
+	cudaError_t rc = scanner->rfn(scanner->st, data_in->ptr, total_out->ptr, numel,
+		clo_sm_count(cq_exec->ctx->dev.ordinal), cq_exec->stream);
+	clo_queue_end(cq_exec, evt);
+	if (clo_cuda_failed(rc, err, "clo_scan_reduce launch")) return NULL;
+	return evt;
+}
+
+/* clo_scan_abstract.c:255-362: alloc in/out, H2D, scan, D2H, block */
+extern "C" cl_bool clo_scan_with_host_data(CloScan* scanner, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		void* data_in, void* data_out, size_t numel, size_t lws_max, GError** err) {
+	if (!scanner || (err && *err)) return CL_FALSE;
+	cl_bool status = CL_FALSE;
+	CCLQueue* intern_queue = NULL;
+	CCLBuffer* in_dev = NULL;
+	CCLBuffer* out_dev = NULL;
+	CCLEvent* evt = NULL;
+	CCLEventWaitList ewl = NULL;
+	GError* ierr = NULL;
+	const size_t in_size = numel * clo_type_sizeof(scanner->elem_type);
+	const size_t out_size = numel * clo_type_sizeof(scanner->sum_type);
+
+	if (cq_exec == NULL) {
+		CCLDevice* dev = ccl_context_get_device(scanner->ctx, 0, &ierr);
+		if (ierr) goto error_handler;
+		intern_queue = ccl_queue_new(scanner->ctx, dev, 0, &ierr);
+		if (ierr) goto error_handler;
+		cq_exec = intern_queue;
+	}
+	if (cq_comm == NULL) cq_comm = cq_exec;
+
+	in_dev = ccl_buffer_new(scanner->ctx, CL_MEM_READ_ONLY, in_size, NULL, &ierr);
+	if (ierr) goto error_handler;
+	out_dev = ccl_buffer_new(scanner->ctx, CL_MEM_READ_WRITE, out_size, NULL, &ierr);
+	if (ierr) goto error_handler;
+
+	evt = ccl_buffer_enqueue_write(in_dev, cq_comm, CL_FALSE, 0, in_size, data_in, NULL, &ierr);
+	if (ierr) goto error_handler;
+	ccl_event_set_name(evt, "write_scan");
+	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
+	if (ierr) goto error_handler;
+
+	evt = scanner->impl_def.scan_with_device_data(scanner, cq_exec, cq_comm, in_dev, out_dev, numel, lws_max, &ierr);
+	if (ierr) goto error_handler;
+
+	evt = ccl_buffer_enqueue_read(out_dev, cq_comm, CL_FALSE, 0, out_size, data_out, ccl_ewl(&ewl, evt, NULL), &ierr);
+	if (ierr) goto error_handler;
+	ccl_event_set_name(evt, "read_scan");
+	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
+	if (ierr) goto error_handler;
+
+	if (scan_check_error_flag(scanner, cq_exec->stream, &ierr)) goto error_handler;
+	status = CL_TRUE;
+	goto finish;
+
+error_handler:
+	g_propagate_error(err, ierr);
+	status = CL_FALSE;
+
+finish:
+	ccl_event_wait_list_clear(&ewl);
+	if (in_dev) ccl_buffer_destroy(in_dev);
+	if (out_dev) ccl_buffer_destroy(out_dev);
+	if (intern_queue) ccl_queue_destroy(intern_queue);
+	return status;
+}
+
+extern "C" CCLContext* clo_scan_get_context(CloScan* s) { return s ? s->ctx : NULL; }
+extern "C" CCLProgram* clo_scan_get_program(CloScan* s) { return s ? s->prg : NULL; }
+extern "C" CloType clo_scan_get_elem_type(CloScan* s) { return s ? s->elem_type : (CloType) -1; }
+extern "C" size_t clo_scan_get_element_size(CloScan* s) { return s ? clo_type_sizeof(s->elem_type) : 0; }
+extern "C" CloType clo_scan_get_sum_type(CloScan* s) { return s ? s->sum_type : (CloType) -1; }
+extern "C" size_t clo_scan_get_sum_size(CloScan* s) { return s ? clo_type_sizeof(s->sum_type) : 0; }
+extern "C" void* clo_scan_get_data(CloScan* s) { return s ? s->data : NULL; }
+extern "C" void clo_scan_set_data(CloScan* s, void* data) { if (s) s->data = data; }
+extern "C" cl_uint clo_scan_get_num_kernels(CloScan* s, GError** err) { return s ? s->impl_def.get_num_kernels(s, err) : 0; }
+extern "C" const char* clo_scan_get_kernel_name(CloScan* s, cl_uint i, GError** err) {
+	return s ? s->impl_def.get_kernel_name(s, i, err) : NULL;
+}
+extern "C" size_t clo_scan_get_localmem_usage(CloScan* s, cl_uint i, size_t lws_max, size_t numel, GError** err) {
+	return s ? s->impl_def.get_localmem_usage(s, i, lws_max, numel, err) : 0;
+}

@@ -1,0 +1,592 @@
+/*
+ * sort.cu -- the sorter object and its four implementations behind the
+ * reference's API (/root/reference/src/cl_ops/sort/clo_sort_abstract.c:91-629,
+ * clo_sort_{sbitonic,abitonic,gselect,satradix}.c).
+ */
+#include "clo_internal.h"
+#include "sort_common.h"
+
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+struct clo_sort {
+	CloSortImplDef impl_def;
+	CCLContext* ctx;
+	CCLProgram* prg;
+	CloType elem_type;
+	CloType key_type;
+	void* data;
+	/* backend */
+	CloKeySpec ks;
+	unsigned radix;          /* satradix "radix=" option (clo_sort_satradix.c:352,385-392) */
+	unsigned minps, maxps, maxsfs;  /* abitonic options, kept as hints */
+	CloRadixState* rs;
+	CloBitonicState* bs;
+};
+
+static ccl_program g_sort_program = { "clo_sort (precompiled sm_100a)" };
+
+/* ------------------------------------------------ macro-string "compilation" */
+
+static std::string squeeze(const char* s) {
+	std::string o;
+	for (; s && *s; ++s) if (!isspace((unsigned char) *s) && *s != '(' && *s != ')') o.push_back(*s);
+	return o;
+}
+
+static bool parse_uint(const std::string& s, size_t& i, uint64_t& v) {
+	size_t start = i;
+	int base = 10;
+	if (s.compare(i, 2, "0x") == 0 || s.compare(i, 2, "0X") == 0) { base = 16; i += 2; start = i; }
+	v = 0;
+	while (i < s.size() && isxdigit((unsigned char) s[i]) && (base == 16 || isdigit((unsigned char) s[i]))) {
+		int d = isdigit((unsigned char) s[i]) ? s[i] - '0' : (tolower(s[i]) - 'a' + 10);
+		v = v * base + (uint64_t) d;
+		++i;
+	}
+	if (i == start) return false;
+	while (i < s.size() && (s[i] == 'u' || s[i] == 'U' || s[i] == 'l' || s[i] == 'L')) ++i;
+	return true;
+}
+
+/* get_key menu: x | x>>K | x&M | x>>K&M  (after removing blanks and parentheses) */
+static bool parse_get_key(const char* get_key, uint32_t& shift, uint64_t& mask) {
+	shift = 0; mask = ~0ull;
+	if (!get_key) return true;
+	std::string s = squeeze(get_key);
+	size_t i = 0;
+	if (s.empty() || s[i] != 'x') return false;
+	++i;
+	if (s.compare(i, 2, ">>") == 0) {
+		i += 2;
+		uint64_t k;
+		if (!parse_uint(s, i, k) || k > 63) return false;
+		shift = (uint32_t) k;
+	}
+	if (i < s.size() && s[i] == '&') {
+		++i;
+		if (!parse_uint(s, i, mask)) return false;
+	}
+	return i == s.size();
+}
+
+/* compare menu: a>b (ascending, the default) | a<b (descending) */
+static bool parse_compare(const char* compare, int& descending) {
+	descending = 0;
+	if (!compare) return true;
+	std::string s = squeeze(compare);
+	if (s == "a>b") return true;
+	if (s == "a<b") { descending = 1; return true; }
+	return false;
+}
+
+static int kind_of(CloType t) {
+	switch (t) {
+	case CLO_CHAR: case CLO_SHORT: case CLO_INT: case CLO_LONG: return CLO_KIND_SIGNED;
+	case CLO_FLOAT: case CLO_DOUBLE: return CLO_KIND_FLOAT;
+	default: return CLO_KIND_UNSIGNED;
+	}
+}
+
+/* ------------------------------------------------------------ option strings */
+
+/* split "k=v,k=v"; returns false on a token that is not key=value */
+static bool next_option(const char*& p, std::string& key, std::string& val, bool& bad) {
+	bad = false;
+	while (*p == ',') ++p;
+	if (!*p) return false;
+	const char* e = strchr(p, ',');
+	std::string tok = e ? std::string(p, e - p) : std::string(p);
+	p = e ? e : p + strlen(p);
+	size_t eq = tok.find('=');
+	if (eq == std::string::npos) { bad = true; key = tok; return true; }
+	key = tok.substr(0, eq); val = tok.substr(eq + 1);
+	return true;
+}
+
+/* ------------------------------------------------------------- satradix */
+
+static const char* satradix_init(CloSort* sorter, const char* options, GError** err) {
+	sorter->radix = 16;
+	if (options) {
+		const char* p = options;
+		std::string k, v; bool bad;
+		while (next_option(p, k, v, bad)) {
+			if (bad) {
+				g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Invalid option '%s' for abitonic sort.", k.c_str());
+				return NULL;
+			}
+			if (k == "radix") {
+				sorter->radix = (unsigned) atoi(v.c_str());
+				if (clo_ones32(sorter->radix) != 1) {
+					g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Radix must be a power of 2.");
+					return NULL;
+				}
+			} else if (k.size() >= 4 && strncasecmp(k.c_str(), "scan", 4) == 0) {
+				/* the reference forwards these to its internal scanner
+				 * (clo_sort_satradix.c:393-406); the onesweep has no scan kernel.
+				 * The scan type is still validated. */
+				if (k.size() == 4 && v != "blelloch") {
+					g_set_error(err, CLO_ERROR, CLO_ERROR_IMPL_NOT_FOUND,
+						"The requested scan implementation, '%s', was not found.", v.c_str());
+					return NULL;
+				}
+			} else {
+				g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Invalid option key '%s' for satradix sort.", k.c_str());
+				return NULL;
+			}
+		}
+	}
+	return "";
+}
+
+static void generic_finalize(CloSort* sorter) { (void) sorter; }
+
+static bool check_buffers(CloSort* sorter, CCLBuffer* in, CCLBuffer* out, size_t numel, GError** err) {
+	const size_t bytes = numel * clo_type_sizeof(sorter->elem_type);
+	if (!in || in->size < bytes || (out && out->size < bytes)) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "sort: buffers too small for %zu elements", numel);
+		return false;
+	}
+	return true;
+}
+
+/* Bits of the promoted key the reference's passes actually sort on:
+ * total_digits * bits_in_digit with total_digits = elem_bits / bits_in_digit
+ * (clo_sort_satradix.c:166-169); shift counts wrap at the promoted key width. */
+static bool satradix_sorted_bits(CloSort* sorter, uint32_t& bits, GError** err) {
+	const unsigned nb = clo_tzc((int) sorter->radix);
+	if (nb == 0) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Radix must be at least 2."); return false; }
+	const unsigned elem_bits = 8 * (unsigned) clo_type_sizeof(sorter->elem_type);
+	const unsigned W = clo_type_sizeof(sorter->key_type) == 8 ? 64 : 32;
+	unsigned sorted = (elem_bits / nb) * nb;
+	if (sorted > W) {
+		if (W % nb) {
+			g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS,
+				"satradix: radix %u with a %u-bit element and a %u-bit key is not supported", sorter->radix, elem_bits, W);
+			return false;
+		}
+		sorted = W;
+	}
+	if (sorted == 0) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "satradix: radix wider than the element"); return false; }
+	bits = sorted;
+	return true;
+}
+
+static CCLEvent* satradix_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		CCLBuffer* data_in, CCLBuffer* data_out, size_t numel, size_t lws_max, GError** err) {
+	(void) cq_comm; (void) lws_max;
+	if ((err && *err) || !cq_exec) return NULL;
+	if (!check_buffers(sorter, data_in, data_out, numel, err)) return NULL;
+	if (sorter->ks.key_kind == CLO_KIND_FLOAT) {
+		/* `key >> b` does not compile for a float key in OpenCL C
+		 * (clo_sort_satradix.cl:61): the reference fails at build time */
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "satradix sorts integer keys only");
+		return NULL;
+	}
+	uint32_t bits = 0;
+	if (!satradix_sorted_bits(sorter, bits, err)) return NULL;
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_radix_onesweep");
+	const char* msg = NULL;
+	void* dst = data_out ? data_out->ptr : data_in->ptr;
+	cudaError_t rc = clo_radix_sort(sorter->rs, clo_sm_count(cq_exec->ctx->dev.ordinal),
+		clo_type_sizeof(sorter->elem_type), sorter->ks, bits, data_in->ptr, dst, NULL, NULL,
+		numel, cq_exec->stream, &msg);
+	clo_queue_end(cq_exec, evt);
+	if (rc != cudaSuccess && msg) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg); return NULL; }
+	if (clo_cuda_failed(rc, err, "clo_radix_sort")) return NULL;
+	return evt;
+}
+
+static const char* const kSatradixKernels[] = { "clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep" };
+
+static cl_uint satradix_get_num_kernels(CloSort* s, GError** err) { (void) s; (void) err; return 3; }
+
+static const char* satradix_get_kernel_name(CloSort* s, cl_uint i, GError** err) {
+	(void) s;
+	if (i >= 3) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
+	return kSatradixKernels[i];
+}
+
+static size_t satradix_get_localmem_usage(CloSort* s, cl_uint i, size_t lws_max, size_t numel, GError** err) {
+	(void) lws_max; (void) numel;
+	const size_t es = clo_type_sizeof(s->elem_type);
+	switch (i) {
+	case 0: return 8 * 256 * 4;
+	case 1: return 8 * 8;
+	case 2: return 16 * 256 * 4 + 256 * 4 + 256 * 8 + 64 + (size_t) 512 * (es == 8 ? 8 : 16) * es;
+	default: g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0;
+	}
+}
+
+extern "C" const CloSortImplDef clo_sort_satradix_def = {
+	"satradix", CL_TRUE, satradix_init, generic_finalize, satradix_sort_with_device_data,
+	satradix_get_num_kernels, satradix_get_kernel_name, satradix_get_localmem_usage
+};
+
+/* -------------------------------------------------------- s/a-bitonic */
+
+static const char* sbitonic_init(CloSort* sorter, const char* options, GError** err) {
+	/* clo_sort_sbitonic.c:140-150 ignores its options */
+	(void) sorter; (void) options; (void) err;
+	return "";
+}
+
+static const char* abitonic_init(CloSort* sorter, const char* options, GError** err) {
+	/* clo_sort_abitonic.c:459-542: minps/maxps in [1,4], maxsfs free, minps <= maxps */
+	sorter->maxps = 4; sorter->minps = 1; sorter->maxsfs = 0xffffffffu;
+	if (options) {
+		const char* p = options;
+		std::string k, v; bool bad;
+		while (next_option(p, k, v, bad)) {
+			if (bad) {
+				g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Invalid option '%s' for abitonic sort.", k.c_str());
+				return NULL;
+			}
+			const unsigned value = (unsigned) atoi(v.c_str());
+			if (k == "minps") {
+				if (value > 4 || value < 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Option 'minps' must be between 1 and 4."); return NULL; }
+				sorter->minps = value;
+			} else if (k == "maxps") {
+				if (value > 4 || value < 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Option 'maxps' must be between 1 and 4."); return NULL; }
+				sorter->maxps = value;
+			} else if (k == "maxsfs") {
+				sorter->maxsfs = value;
+			} else {
+				g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Invalid option key '%s' for abitonic sort.", k.c_str());
+				return NULL;
+			}
+		}
+		if (sorter->maxps < sorter->minps) {
+			g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "'minps' (%d) must be less or equal than 'maxps' (%d).",
+				(int) sorter->minps, (int) sorter->maxps);
+			return NULL;
+		}
+	}
+	return "";
+}
+
+static CCLEvent* bitonic_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		CCLBuffer* data_in, CCLBuffer* data_out, size_t numel, size_t lws_max, GError** err) {
+	(void) cq_comm; (void) lws_max;
+	if ((err && *err) || !cq_exec) return NULL;
+	if (!check_buffers(sorter, data_in, data_out, numel, err)) return NULL;
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	const size_t bytes = numel * clo_type_sizeof(sorter->elem_type);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_bitonic");
+	cudaError_t rc = cudaSuccess;
+	void* work = data_in->ptr;
+	if (data_out && data_out->ptr != data_in->ptr) {
+		/* clo_sort_sbitonic.c:83-96: copy, then sort the copy */
+		rc = cudaMemcpyAsync(data_out->ptr, data_in->ptr, bytes, cudaMemcpyDeviceToDevice, cq_exec->stream);
+		work = data_out->ptr;
+	}
+	if (rc == cudaSuccess)
+		rc = clo_bitonic_sort(sorter->bs, clo_type_sizeof(sorter->elem_type), sorter->ks, work, numel, cq_exec->stream);
+	clo_queue_end(cq_exec, evt);
+	if (clo_cuda_failed(rc, err, "clo_bitonic_sort")) return NULL;
+	return evt;
+}
+
+static const char* const kBitonicKernels[] = { "clo_bitonic_local", "clo_bitonic_global" };
+
+static cl_uint bitonic_get_num_kernels(CloSort* s, GError** err) { (void) s; (void) err; return 2; }
+
+static const char* bitonic_get_kernel_name(CloSort* s, cl_uint i, GError** err) {
+	(void) s;
+	if (i >= 2) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
+	return kBitonicKernels[i];
+}
+
+static size_t bitonic_get_localmem_usage(CloSort* s, cl_uint i, size_t lws_max, size_t numel, GError** err) {
+	(void) lws_max; (void) numel;
+	if (i >= 2) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
+	return i == 0 ? 4096 * clo_type_sizeof(s->elem_type) : 0;
+}
+
+extern "C" const CloSortImplDef clo_sort_sbitonic_def = {
+	"sbitonic", CL_TRUE, sbitonic_init, generic_finalize, bitonic_sort_with_device_data,
+	bitonic_get_num_kernels, bitonic_get_kernel_name, bitonic_get_localmem_usage
+};
+
+extern "C" const CloSortImplDef clo_sort_abitonic_def = {
+	"abitonic", CL_TRUE, abitonic_init, generic_finalize, bitonic_sort_with_device_data,
+	bitonic_get_num_kernels, bitonic_get_kernel_name, bitonic_get_localmem_usage
+};
+
+/* -------------------------------------------------------------- gselect */
+
+static const char* gselect_init(CloSort* sorter, const char* options, GError** err) {
+	/* clo_sort_gselect.c:150-160 ignores its options */
+	(void) sorter; (void) options; (void) err;
+	return "";
+}
+
+static CCLEvent* gselect_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		CCLBuffer* data_in, CCLBuffer* data_out, size_t numel, size_t lws_max, GError** err) {
+	(void) cq_comm; (void) lws_max;
+	if ((err && *err) || !cq_exec) return NULL;
+	if (!check_buffers(sorter, data_in, data_out, numel, err)) return NULL;
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	const size_t es = clo_type_sizeof(sorter->elem_type), bytes = numel * es;
+	void* tmp = NULL;
+	void* out = data_out ? data_out->ptr : NULL;
+	if (!out || out == data_in->ptr) {
+		/* clo_sort_gselect.c:60-70,117-124: no output buffer -> temporary + copy back */
+		if (clo_cuda_failed(cudaMallocAsync(&tmp, bytes ? bytes : 1, cq_exec->stream), err, "cudaMallocAsync")) return NULL;
+		out = tmp;
+	}
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_gselect");
+	cudaError_t rc = clo_gselect_sort(es, sorter->ks, data_in->ptr, out, numel, cq_exec->stream);
+	if (rc == cudaSuccess && tmp)
+		rc = cudaMemcpyAsync(data_in->ptr, tmp, bytes, cudaMemcpyDeviceToDevice, cq_exec->stream);
+	if (tmp) cudaFreeAsync(tmp, cq_exec->stream);
+	clo_queue_end(cq_exec, evt);
+	if (clo_cuda_failed(rc, err, "clo_gselect_sort")) return NULL;
+	return evt;
+}
+
+static const char* const kGselectKernels[] = { "clo_gselect_kernel" };
+
+static cl_uint gselect_get_num_kernels(CloSort* s, GError** err) { (void) s; (void) err; return 1; }
+
+static const char* gselect_get_kernel_name(CloSort* s, cl_uint i, GError** err) {
+	(void) s;
+	if (i >= 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
+	return kGselectKernels[i];
+}
+
+static size_t gselect_get_localmem_usage(CloSort* s, cl_uint i, size_t lws_max, size_t numel, GError** err) {
+	(void) s; (void) lws_max; (void) numel;
+	if (i >= 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
+	return 256 * 8;
+}
+
+extern "C" const CloSortImplDef clo_sort_gselect_def = {
+	"gselect", CL_FALSE, gselect_init, generic_finalize, gselect_sort_with_device_data,
+	gselect_get_num_kernels, gselect_get_kernel_name, gselect_get_localmem_usage
+};
+
+/* --------------------------------------------------------------- object */
+
+extern "C" CloSort* clo_sort_new(const char* type, const char* options, CCLContext* ctx,
+		CloType* elem_type, CloType* key_type, const char* compare, const char* get_key,
+		const char* compiler_opts, GError** err) {
+	(void) compiler_opts; /* OpenCL build options: accepted and ignored */
+	if (err && *err) return NULL;
+	if (!ctx || !elem_type) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "NULL context or element type"); return NULL; }
+	const CloSortImplDef* impls[] = { &clo_sort_sbitonic_def, &clo_sort_abitonic_def,
+		&clo_sort_gselect_def, &clo_sort_satradix_def };
+	const CloSortImplDef* def = NULL;
+	for (const CloSortImplDef* d : impls) if (type && strcmp(type, d->name) == 0) def = d;
+	if (!def) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_IMPL_NOT_FOUND,
+			"The requested sort implementation, '%s', was not found.", type ? type : "(null)");
+		return NULL;
+	}
+	const CloType et = *elem_type, kt = key_type ? *key_type : *elem_type;
+	if (clo_type_sizeof(et) == 0 || clo_type_sizeof(kt) == 0 || et == CLO_HALF || kt == CLO_HALF) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_UNKNOWN_TYPE, "Unsupported sort types (elem=%d, key=%d)", (int) et, (int) kt);
+		return NULL;
+	}
+	clo_sort* s = new clo_sort();
+	s->impl_def = *def;
+	s->ctx = ctx; ccl_context_ref(ctx);
+	s->prg = &g_sort_program;
+	s->elem_type = et; s->key_type = kt;
+	s->data = NULL;
+	s->radix = 16; s->minps = 1; s->maxps = 4; s->maxsfs = 0xffffffffu;
+	s->rs = clo_radix_state_new();
+	s->bs = clo_bitonic_state_new();
+
+	GError* ierr = NULL;
+	uint32_t shift = 0; uint64_t mask = ~0ull; int desc = 0;
+	s->impl_def.init(s, options, &ierr);
+	if (!ierr && !parse_get_key(get_key, shift, mask))
+		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
+			"get_key '%s' is not supported (menu: (x), ((x) >> K), ((x) & M), (((x) >> K) & M))", get_key);
+	if (!ierr && !parse_compare(compare, desc))
+		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
+			"compare '%s' is not supported (menu: ((a) > (b)), ((a) < (b)))", compare);
+	if (!ierr && kind_of(et) == CLO_KIND_FLOAT && (shift != 0 || mask != ~0ull || kt != et))
+		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS, "a floating-point element only supports the identity key");
+	if (ierr) { g_propagate_error(err, ierr); clo_sort_destroy(s); return NULL; }
+
+	CloKeySpec& ks = s->ks;
+	ks.mask = mask; ks.shift = shift;
+	ks.elem_bits = 8 * (uint32_t) clo_type_sizeof(et);
+	ks.key_bits = 8 * (uint32_t) clo_type_sizeof(kt);
+	ks.elem_signed = kind_of(et) == CLO_KIND_SIGNED;
+	ks.key_kind = kind_of(kt);
+	ks.descending = desc;
+	ks.identity = (shift == 0 && mask == ~0ull && ks.key_bits == ks.elem_bits &&
+		kind_of(et) != CLO_KIND_FLOAT) ? 1 : 0;
+	if (kind_of(et) == CLO_KIND_FLOAT) ks.identity = 1;  /* raw bits are the key bits */
+	clo_handle_add(s);
+	return s;
+}
+
+extern "C" void clo_sort_destroy(CloSort* sorter) {
+	if (!sorter) return;
+	clo_handle_remove(sorter);
+	sorter->impl_def.finalize(sorter);
+	{
+		CloDeviceGuard g(sorter->ctx->dev.ordinal);
+		clo_radix_state_free(sorter->rs);
+		clo_bitonic_state_free(sorter->bs);
+	}
+	ccl_context_unref(sorter->ctx);
+	delete sorter;
+}
+
+extern "C" CCLEvent* clo_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		CCLBuffer* data_in, CCLBuffer* data_out, size_t numel, size_t lws_max, GError** err) {
+	if (!sorter || (err && *err) || !cq_exec) return NULL;
+	return sorter->impl_def.sort_with_device_data(sorter, cq_exec, cq_comm, data_in, data_out, numel, lws_max, err);
+}
+
+/* clo_sort_abstract.c:296-418 */
+extern "C" cl_bool clo_sort_with_host_data(CloSort* sorter, CCLQueue* cq_exec, CCLQueue* cq_comm,
+		void* data_in, void* data_out, size_t numel, size_t lws_max, GError** err) {
+	if (!sorter || (err && *err)) return CL_FALSE;
+	cl_bool status = CL_FALSE;
+	CCLBuffer* in_dev = NULL;
+	CCLBuffer* aux_dev = NULL;
+	CCLBuffer* out_dev = NULL;
+	CCLBuffer* read_dev = NULL;
+	CCLQueue* intern_queue = NULL;
+	CCLEvent* evt = NULL;
+	CCLEventWaitList ewl = NULL;
+	GError* ierr = NULL;
+	const size_t data_size = numel * clo_type_sizeof(sorter->elem_type);
+
+	if (cq_exec == NULL) {
+		CCLDevice* dev = ccl_context_get_device(sorter->ctx, 0, &ierr);
+		if (ierr) goto error_handler;
+		intern_queue = ccl_queue_new(sorter->ctx, dev, 0, &ierr);
+		if (ierr) goto error_handler;
+		cq_exec = intern_queue;
+	}
+	if (cq_comm == NULL) cq_comm = cq_exec;
+
+	in_dev = ccl_buffer_new(sorter->ctx, CL_MEM_READ_WRITE, data_size, NULL, &ierr);
+	if (ierr) goto error_handler;
+	if (!sorter->impl_def.in_place) {
+		aux_dev = ccl_buffer_new(sorter->ctx, CL_MEM_READ_WRITE, data_size, NULL, &ierr);
+		if (ierr) goto error_handler;
+		out_dev = aux_dev;
+		read_dev = aux_dev;
+	} else {
+		read_dev = in_dev;
+	}
+
+	evt = ccl_buffer_enqueue_write(in_dev, cq_comm, CL_FALSE, 0, data_size, data_in, NULL, &ierr);
+	if (ierr) goto error_handler;
+	ccl_event_set_name(evt, "write_sort");
+	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
+	if (ierr) goto error_handler;
+
+	evt = sorter->impl_def.sort_with_device_data(sorter, cq_exec, cq_comm, in_dev, out_dev, numel, lws_max, &ierr);
+	if (ierr) goto error_handler;
+
+	evt = ccl_buffer_enqueue_read(read_dev, cq_comm, CL_FALSE, 0, data_size, data_out, ccl_ewl(&ewl, evt, NULL), &ierr);
+	if (ierr) goto error_handler;
+	ccl_event_set_name(evt, "read_sort");
+	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
+	if (ierr) goto error_handler;
+
+	if (clo_radix_status(sorter->rs, cq_exec->stream) != 0) {
+		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_LIBRARY, "radix look-back timed out (device status flag set)");
+		goto error_handler;
+	}
+	status = CL_TRUE;
+	goto finish;
+
+error_handler:
+	g_propagate_error(err, ierr);
+	status = CL_FALSE;
+
+finish:
+	ccl_event_wait_list_clear(&ewl);
+	if (in_dev) ccl_buffer_destroy(in_dev);
+	if (aux_dev) ccl_buffer_destroy(aux_dev);
+	if (intern_queue) ccl_queue_destroy(intern_queue);
+	return status;
+}
+
+extern "C" CCLContext* clo_sort_get_context(CloSort* s) { return s ? s->ctx : NULL; }
+extern "C" CCLProgram* clo_sort_get_program(CloSort* s) { return s ? s->prg : NULL; }
+extern "C" CloType clo_sort_get_element_type(CloSort* s) { return s ? s->elem_type : (CloType) -1; }
+extern "C" size_t clo_sort_get_element_size(CloSort* s) { return s ? clo_type_sizeof(s->elem_type) : 0; }
+extern "C" CloType clo_sort_get_key_type(CloSort* s) { return s ? s->key_type : (CloType) -1; }
+extern "C" size_t clo_sort_get_key_size(CloSort* s) { return s ? clo_type_sizeof(s->key_type) : 0; }
+extern "C" void* clo_sort_get_data(CloSort* s) { return s ? s->data : NULL; }
+extern "C" void clo_sort_set_data(CloSort* s, void* data) { if (s) s->data = data; }
+extern "C" cl_uint clo_sort_get_num_kernels(CloSort* s, GError** err) { return s ? s->impl_def.get_num_kernels(s, err) : 0; }
+extern "C" const char* clo_sort_get_kernel_name(CloSort* s, cl_uint i, GError** err) {
+	return s ? s->impl_def.get_kernel_name(s, i, err) : NULL;
+}
+extern "C" size_t clo_sort_get_localmem_usage(CloSort* s, cl_uint i, size_t lws_max, size_t numel, GError** err) {
+	return s ? s->impl_def.get_localmem_usage(s, i, lws_max, numel, err) : 0;
+}
+
+/* ------------------------------------------------ additive entry points */
+
+extern "C" CCLEvent* clo_sort_pairs_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+		CCLBuffer* keys, CCLBuffer* payload, size_t numel, GError** err) {
+	if (!sorter || (err && *err) || !cq_exec) return NULL;
+	const size_t ks_bytes = clo_type_sizeof(sorter->elem_type);
+	if (!keys || !payload || keys->size < numel * ks_bytes || payload->size < numel * sizeof(cl_uint)) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "sort pairs: buffers too small for %zu pairs", numel);
+		return NULL;
+	}
+	if (ks_bytes != 4 && ks_bytes != 8) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "sort pairs: keys must be 4 or 8 bytes wide");
+		return NULL;
+	}
+	if (sorter->ks.key_kind == CLO_KIND_FLOAT) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "sort pairs: integer keys only");
+		return NULL;
+	}
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_radix_onesweep_pairs");
+	const char* msg = NULL;
+	cudaError_t rc = clo_radix_sort(sorter->rs, clo_sm_count(cq_exec->ctx->dev.ordinal), ks_bytes, sorter->ks,
+		(uint32_t) (8 * ks_bytes), keys->ptr, keys->ptr, (const uint32_t*) payload->ptr, (uint32_t*) payload->ptr,
+		numel, cq_exec->stream, &msg);
+	clo_queue_end(cq_exec, evt);
+	if (rc != cudaSuccess && msg) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg); return NULL; }
+	if (clo_cuda_failed(rc, err, "clo_radix_sort (pairs)")) return NULL;
+	return evt;
+}
+
+extern "C" CCLEvent* clo_sort_partition_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+		CCLBuffer* keys_in, CCLBuffer* payload_in, CCLBuffer* keys_out, CCLBuffer* payload_out,
+		size_t numel, cl_ulong gidx0, CCLBuffer* splitter_keys, CCLBuffer* splitter_idx, cl_uint nparts,
+		CCLBuffer* counts_out, GError** err) {
+	if (!sorter || (err && *err) || !cq_exec) return NULL;
+	const size_t kb = clo_type_sizeof(sorter->elem_type);
+	if (!keys_in || !keys_out || !counts_out || keys_in->size < numel * kb || keys_out->size < numel * kb ||
+			counts_out->size < nparts * sizeof(cl_ulong) ||
+			(nparts > 1 && (!splitter_keys || !splitter_idx || splitter_keys->size < (nparts - 1) * kb ||
+				splitter_idx->size < (nparts - 1) * sizeof(cl_ulong))) ||
+			((payload_in == NULL) != (payload_out == NULL))) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "partition: invalid buffers");
+		return NULL;
+	}
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_radix_partition");
+	const char* msg = NULL;
+	cudaError_t rc = clo_radix_partition(sorter->rs, kb, keys_in->ptr,
+		payload_in ? (const uint32_t*) payload_in->ptr : NULL, keys_out->ptr,
+		payload_out ? (uint32_t*) payload_out->ptr : NULL, numel, gidx0,
+		splitter_keys ? splitter_keys->ptr : NULL, splitter_idx ? (const uint64_t*) splitter_idx->ptr : NULL,
+		nparts, (uint64_t*) counts_out->ptr, cq_exec->stream, &msg);
+	clo_queue_end(cq_exec, evt);
+	if (rc != cudaSuccess && msg) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg); return NULL; }
+	if (clo_cuda_failed(rc, err, "clo_radix_partition")) return NULL;
+	return evt;
+}

@@ -1,0 +1,90 @@
+/*
+ * sort_common.h -- shared between the sorter object (sort.cu) and the sort
+ * kernels (radix.cu, bitonic.cu): the key-extraction spec standing in for the
+ * reference's CLO_SORT_KEY_GET / CLO_SORT_COMPARE macro strings
+ * (/root/reference/src/cl_ops/sort/clo_sort_abstract.c:144-168).
+ */
+#ifndef CLO_SORT_COMMON_H
+#define CLO_SORT_COMMON_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+enum { CLO_KIND_UNSIGNED = 0, CLO_KIND_SIGNED = 1, CLO_KIND_FLOAT = 2 };
+
+/* key = (KEY_TYPE) (((x) >> shift) & mask), x of the element type */
+struct CloKeySpec {
+	uint64_t mask;        /* all ones: no mask */
+	uint32_t shift;
+	uint32_t elem_bits;   /* 8 * sizeof(elem) */
+	uint32_t key_bits;    /* 8 * sizeof(key) */
+	int elem_signed;      /* arithmetic >> and sign extension of the element */
+	int key_kind;         /* CLO_KIND_* of the key type */
+	int descending;       /* compare "((a) < (b))" */
+	int identity;         /* shift == 0, no mask, key type == elem type */
+};
+
+#ifdef __CUDACC__
+/* raw element bits (zero extended) -> raw key bits (zero extended, key_bits wide) */
+__host__ __device__ inline uint64_t clo_extract_key(uint64_t raw, const CloKeySpec& ks) {
+	if (ks.identity) return raw;
+	uint64_t x = raw;
+	if (ks.elem_signed && ks.elem_bits < 64) {
+		const int sh = 64 - (int) ks.elem_bits;
+		x = (uint64_t) (((int64_t) (raw << sh)) >> sh);
+	}
+	if (ks.elem_signed) x = (uint64_t) (((int64_t) x) >> ks.shift);
+	else x = x >> ks.shift;
+	x &= ks.mask;
+	if (ks.key_bits < 64) x &= ((1ull << ks.key_bits) - 1);
+	return x;
+}
+
+/* raw key bits -> unsigned 64-bit value whose natural order is the typed
+ * "a > b" order of the key type (-0.0 == +0.0; NaN keys are not supported) */
+__host__ __device__ inline uint64_t clo_ordered_key(uint64_t k, const CloKeySpec& ks) {
+	if (ks.key_kind == CLO_KIND_SIGNED) {
+		k ^= (1ull << (ks.key_bits - 1));
+	} else if (ks.key_kind == CLO_KIND_FLOAT) {
+		const uint64_t sign = 1ull << (ks.key_bits - 1);
+		const uint64_t all = ks.key_bits < 64 ? ((1ull << ks.key_bits) - 1) : ~0ull;
+		if (k == sign) k = 0;                       /* -0.0 -> +0.0 */
+		k = (k & sign) ? (~k & all) : (k | sign);
+	}
+	return ks.descending ? ~k : k;
+}
+#endif
+
+/* per-sorter scratch for the radix path, defined in radix.cu */
+struct CloRadixState;
+CloRadixState* clo_radix_state_new();
+void clo_radix_state_free(CloRadixState* st);
+
+/* Sort `n` elements of `elem_size` bytes (1,2,4,8) by the low `sorted_bits` bits
+ * of the promoted key (see radix.cu).  src is never written unless src == dst
+ * (in place).  payload_* may be NULL (keys only); payload is 32-bit.
+ * Returns cudaSuccess or an error; *err_msg names unsupported configurations. */
+cudaError_t clo_radix_sort(CloRadixState* st, int sm_count, size_t elem_size, const CloKeySpec& ks,
+	uint32_t sorted_bits, const void* src, void* dst, const uint32_t* payload_src, uint32_t* payload_dst,
+	size_t n, cudaStream_t stream, const char** err_msg);
+
+/* Stable multi-way partition by splitters (sample sort); see radix.cu. */
+cudaError_t clo_radix_partition(CloRadixState* st, size_t elem_size, const void* keys_in,
+	const uint32_t* payload_in, void* keys_out, uint32_t* payload_out, size_t n, uint64_t gidx0,
+	const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out,
+	cudaStream_t stream, const char** err_msg);
+
+/* device status flag of the last radix call (0 = ok); synchronises the stream */
+int clo_radix_status(CloRadixState* st, cudaStream_t stream);
+
+/* bitonic / gselect, defined in bitonic.cu */
+struct CloBitonicState;
+CloBitonicState* clo_bitonic_state_new();
+void clo_bitonic_state_free(CloBitonicState* st);
+cudaError_t clo_bitonic_sort(CloBitonicState* st, size_t elem_size, const CloKeySpec& ks,
+	void* data, size_t n, cudaStream_t stream);
+cudaError_t clo_gselect_sort(size_t elem_size, const CloKeySpec& ks, const void* in, void* out,
+	size_t n, cudaStream_t stream);
+
+#endif

@@ -1,0 +1,73 @@
+/*
+ * include/cl_ops/clo_b200.h -- additive entry points that have no counterpart in
+ * the reference API but that its callers need on this backend (SURVEY.md 8b,
+ * "necessary additive exports").
+ */
+#ifndef CLO_B200_EXT_H
+#define CLO_B200_EXT_H
+
+#include <cl_ops/clo_common.h>
+#include <cl_ops/clo_rng.h>
+#include <cl_ops/clo_sort_abstract.h>
+#include <cl_ops/clo_scan_abstract.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Bulk generation.  The reference has no host-side generate call; the bulk
+ * layout is defined by its benchmark driver, which relaunches a one-number-per-
+ * stream kernel `runs` times (src/benchmarks/clo_rng_bench.cl:23-37,
+ * src/benchmarks/clo_rng_bench.c:302-324):
+ *   out[r * G + g] = next_r(state_g) >> (32 - bits)      when maxint == 0
+ *                  = next_r(state_g) % maxint            otherwise
+ * for r < runs, g < G = seeds_count.  States are written back, so a second call
+ * continues every stream where the first stopped. `out` holds runs*G cl_uint. */
+CCLEvent* clo_rng_generate(CloRng* rng, CCLQueue* cq, CCLBuffer* out,
+	size_t runs, cl_uint bits, cl_uint maxint, GError** err);
+/* Same with a host destination (allocates, generates, copies back, blocks). */
+cl_bool clo_rng_generate_host(CloRng* rng, CCLQueue* cq, void* out,
+	size_t runs, cl_uint bits, cl_uint maxint, GError** err);
+/* Multi-GPU stream partitioning: like clo_rng_new(DEV_GID) but the seeds are
+ * those of global work-items [gid_offset, gid_offset + seeds_count)
+ * (clo_rng_init.cl:52: seed = get_global_id(0) + main_seed). */
+CloRng* clo_rng_new_dev_gid_offset(const char* type, size_t seeds_count,
+	cl_ulong gid_offset, cl_ulong main_seed, const char* hash,
+	CCLContext* ctx, CCLQueue* cq, GError** err);
+
+/* Key/payload sort with the payload in a separate array (CloType is scalar,
+ * so "u64 key + u32 payload" cannot be expressed through clo_sort_new's element
+ * type).  Uses the sorter's key type for `keys`; `payload` is cl_uint.  Stable,
+ * raw key bits ascending (satradix semantics).  In place (aux buffers cached). */
+CCLEvent* clo_sort_pairs_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+	CCLBuffer* keys, CCLBuffer* payload, size_t numel, GError** err);
+
+/* Scan building blocks for the multi-GPU scan (per-GPU total, then a scan
+ * with a carry-in held in device memory).  `total_out` / `carry_in` point to one
+ * value of the scanner's sum type in device memory; carry_in may be NULL. */
+CCLEvent* clo_scan_reduce_with_device_data(CloScan* scanner, CCLQueue* cq_exec,
+	CCLBuffer* data_in, CCLBuffer* total_out, size_t numel, GError** err);
+CCLEvent* clo_scan_with_device_data_carry(CloScan* scanner, CCLQueue* cq_exec,
+	CCLBuffer* data_in, CCLBuffer* data_out, CCLBuffer* carry_in,
+	size_t numel, GError** err);
+
+/* Sample-sort building block: stable partition of (keys[, payload]) into
+ * `nparts` contiguous buckets by `nparts-1` splitters.  Element i (global index
+ * gidx0+i) goes to bucket #{ s : (splitter_key[s], splitter_idx[s]) <= (key_i, gidx0+i) }.
+ * counts_out receives nparts cl_ulong bucket sizes (device memory). */
+CCLEvent* clo_sort_partition_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+	CCLBuffer* keys_in, CCLBuffer* payload_in, CCLBuffer* keys_out,
+	CCLBuffer* payload_out, size_t numel, cl_ulong gidx0,
+	CCLBuffer* splitter_keys, CCLBuffer* splitter_idx, cl_uint nparts,
+	CCLBuffer* counts_out, GError** err);
+
+/* Library / device info. */
+const char* clo_b200_version(void);
+/* number of this library's kernels launched since load (bench evidence) */
+cl_ulong clo_b200_launch_count(void);
+void clo_b200_error_free(GError* err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

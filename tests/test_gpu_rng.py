@@ -1,0 +1,92 @@
+"""GPU parity: clo_rng seeding and bulk generation vs the CPU oracle -- bit-exact for
+every generator, seed mode, hash, and for the states left behind."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RNGS = oracle.RNG_NAMES
+HASHES = [(None, 0), ("KNUTH(x)", 1), ("XS1(x)", 2)]
+
+
+@pytest.mark.parametrize("rng", RNGS)
+@pytest.mark.parametrize("hash_name,hash_id", HASHES)
+@pytest.mark.parametrize("G,runs", [(1, 4), (5, 3), (1024, 16), (10000, 7), (65536 + 4, 5)])
+def test_dev_gid_streams(clo, ctx, queue, rng, hash_name, hash_id, G, runs):
+    main_seed = 1234
+    r = clo.CloRng(rng, ctx, clo.SEED_DEV_GID, None, G, main_seed, hash_name, queue)
+    st0 = oracle.rng_seeds_dev_gid(rng, hash_id, main_seed, G)
+    assert np.array_equal(r.read_seeds(queue), st0), "seed init differs"
+    got = r.generate_host(runs, queue=queue)
+    want, st1 = oracle.rng_generate(rng, st0, G, runs)
+    assert np.array_equal(got, want)
+    assert np.array_equal(r.read_seeds(queue), st1), "states after generate differ"
+    # a second call continues every stream
+    got2 = r.generate_host(2, queue=queue)
+    want2, _ = oracle.rng_generate(rng, st1, G, 2)
+    assert np.array_equal(got2, want2)
+    r.destroy()
+
+
+@pytest.mark.parametrize("rng", RNGS)
+def test_host_mt_and_ext_host_seeds(clo, ctx, queue, rng):
+    G = 4096
+    r = clo.CloRng(rng, ctx, clo.SEED_HOST_MT, None, G, 0, None, queue)
+    st0 = oracle.rng_seeds_host_mt(rng, 0, G)
+    assert np.array_equal(r.read_seeds(queue), st0)
+    got = r.generate_host(9, queue=queue)
+    want, _ = oracle.rng_generate(rng, st0, G, 9)
+    assert np.array_equal(got, want)
+    r.destroy()
+    # EXT_HOST with the byte pattern of the reference's test (test_rng.c:267-268)
+    ss = oracle.RNG_SEED_SIZE[rng]
+    pat = (((np.arange(G * ss) + 1) * 3) & 0xFF).astype(np.uint8)
+    r = clo.CloRng(rng, ctx, clo.SEED_EXT_HOST, pat, G, 0, None, queue)
+    got = r.generate_host(5, queue=queue)
+    want, _ = oracle.rng_generate(rng, pat, G, 5)
+    assert np.array_equal(got, want)
+    r.destroy()
+
+
+@pytest.mark.parametrize("rng", ["lcg", "xorshift128", "mwc64x"])
+def test_bits_and_maxint(clo, ctx, queue, rng):
+    G = 2048
+    st0 = oracle.rng_seeds_dev_gid(rng, 1, 7, G)
+    r = clo.CloRng(rng, ctx, clo.SEED_DEV_GID, None, G, 7, "KNUTH(x)", queue)
+    got = r.generate_host(6, bits=8, queue=queue)
+    want, st1 = oracle.rng_generate(rng, st0, G, 6, bits=8)
+    assert np.array_equal(got, want)
+    got = r.generate_host(6, maxint=1000, queue=queue)
+    want, _ = oracle.rng_generate(rng, st1, G, 6, maxint=1000)
+    assert np.array_equal(got, want)
+    r.destroy()
+
+
+def test_gid_offset_partition_equals_whole(clo, ctx, queue):
+    """multi-GPU stream partitioning: streams [off, off+G/2) seeded with a gid offset
+    reproduce the second half of the single-device streams (no communication)."""
+    G = 8192
+    whole = clo.CloRng("xorshift128", ctx, clo.SEED_DEV_GID, None, G, 5, "KNUTH(x)", queue)
+    w = whole.generate_host(4, queue=queue)
+    half = clo.CloRng("xorshift128", ctx, seeds_count=G // 2, main_seed=5, hash="KNUTH(x)", queue=queue,
+                      gid_offset=G // 2)
+    h = half.generate_host(4, queue=queue)
+    assert np.array_equal(w[:, G // 2:], h)
+    whole.destroy()
+    half.destroy()
+
+
+def test_rng_errors_and_source(clo, ctx, queue):
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloRng("nosuchrng", ctx, clo.SEED_DEV_GID, None, 16, 0, None, queue)
+    assert ei.value.code == clo.CLO_ERROR_IMPL_NOT_FOUND
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloRng("lcg", ctx, clo.SEED_EXT_HOST, None, 16, 0, None, queue)
+    assert ei.value.code == clo.CLO_ERROR_ARGS
+    r = clo.CloRng("mwc64x", ctx, clo.SEED_DEV_GID, None, 16, 0, "(x * 3 + 1)", queue)  # test_rng.c:42 no-op hash
+    assert r.get_size() == 16 * 8
+    assert "clo_rng_next" in r.get_source()
+    assert np.array_equal(r.read_seeds(queue), oracle.rng_seeds_dev_gid("mwc64x", 0, 0, 16))
+    r.destroy()

@@ -1,0 +1,107 @@
+"""GPU parity: clo_scan (single-pass look-back kernel) vs the CPU oracle, through the C-ABI.
+
+Bar: bit-exact for integer sums (any wrap-around included); float sums within
+|gpu - ref| <= 1e-5 * |ref| + 1e-3 of a double-precision host prefix sum.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [1, 2, 3, 31, 257, 4096, 4097, 12289, 100003, (1 << 20) + 3]
+INT_PAIRS = [(oracle.UINT, oracle.UINT), (oracle.UINT, oracle.ULONG), (oracle.INT, oracle.LONG),
+             (oracle.UCHAR, oracle.UINT), (oracle.USHORT, oracle.ULONG), (oracle.ULONG, oracle.ULONG),
+             (oracle.CHAR, oracle.INT), (oracle.LONG, oracle.UINT), (oracle.SHORT, oracle.USHORT),
+             (oracle.UINT, oracle.UCHAR)]
+
+
+def _rand(rng, ctype, n, full_range):
+    dt = oracle.NP_TYPES[ctype]
+    if np.issubdtype(dt, np.integer):
+        info = np.iinfo(dt)
+        if full_range:
+            return rng.integers(info.min, info.max, size=n, dtype=dt, endpoint=True)
+        return rng.integers(0, 128, size=n).astype(dt)
+    return rng.random(n).astype(dt)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("et,st", INT_PAIRS)
+def test_scan_int_bit_exact(clo, ctx, queue, et, st, n):
+    rng = np.random.default_rng(1000 + n + 31 * et + 7 * st)
+    for full_range in (False, True):
+        a = _rand(rng, et, n, full_range)
+        s = clo.CloScan("blelloch", ctx, et, st)
+        got = s.with_host_data(a, queue)
+        s.destroy()
+        want = oracle.scan(a, et, st)
+        assert got.dtype == want.dtype
+        assert np.array_equal(got, want), "scan %s->%s n=%d full=%s first diff at %d" % (
+            oracle.TYPE_NAMES[et], oracle.TYPE_NAMES[st], n, full_range,
+            int(np.flatnonzero(got != want)[0]))
+
+
+def test_scan_bench_input_matches_serial_host_scan(clo, ctx, queue):
+    """The reference's own acceptance check (clo_scan_bench.c:246-271): uint -> ulong,
+    values in [0,128) from GRand seed 0, exact equality with a serial host scan."""
+    a = oracle.scan_input(0, oracle.UINT, 1 << 18)
+    s = clo.CloScan("blelloch", ctx, oracle.UINT, oracle.ULONG)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    want = np.concatenate(([0], np.cumsum(a.astype(np.uint64))[:-1])).astype(np.uint64)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n", [1, 1000, 4097, (1 << 20) + 3, 1 << 22])
+@pytest.mark.parametrize("et,st", [(oracle.FLOAT, oracle.FLOAT), (oracle.FLOAT, oracle.DOUBLE),
+                                   (oracle.DOUBLE, oracle.DOUBLE), (oracle.UINT, oracle.FLOAT)])
+def test_scan_float_tolerance(clo, ctx, queue, et, st, n):
+    rng = np.random.default_rng(77 + n)
+    a = _rand(rng, et, n, False)
+    s = clo.CloScan("blelloch", ctx, et, st)
+    got = s.with_host_data(a, queue).astype(np.float64)
+    s.destroy()
+    ref = oracle.scan_f64ref(a, et)
+    tol = 1e-5 * np.abs(ref) + 1e-3
+    err = np.abs(got - ref)
+    assert np.all(err <= tol), "max err %.3e (rel %.3e)" % (err.max(), (err / np.maximum(np.abs(ref), 1)).max())
+
+
+def test_scan_device_data_carry_and_reduce(clo, ctx, queue):
+    """device-data entry point on wrapped torch memory; carry-in and reduce are the
+    building blocks of the multi-GPU scan."""
+    import torch
+    n = (1 << 21) + 17
+    a = oracle.scan_input(3, oracle.UINT, n)
+    t_in = torch.from_numpy(a.view(np.int32)).cuda()
+    t_out = torch.empty(n, dtype=torch.int64, device="cuda")
+    t_carry = torch.tensor([123456789012], dtype=torch.int64, device="cuda")
+    t_total = torch.zeros(1, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+    b_carry, b_total = clo.Buffer.wrap_tensor(ctx, t_carry), clo.Buffer.wrap_tensor(ctx, t_total)
+    s = clo.CloScan("blelloch", ctx, oracle.UINT, oracle.ULONG)
+    s.with_device_data(queue, b_in, b_out, n, carry_in=b_carry)
+    s.reduce_with_device_data(queue, b_in, b_total, n)
+    queue.finish()
+    want = oracle.scan(a, oracle.UINT, oracle.ULONG) + np.uint64(123456789012)
+    assert np.array_equal(t_out.cpu().numpy().view(np.uint64), want)
+    assert int(t_total.item()) == int(a.astype(np.uint64).sum())
+    # second call on the same scanner (epoch / ticket bookkeeping)
+    s.with_device_data(queue, b_in, b_out, n)
+    queue.finish()
+    assert np.array_equal(t_out.cpu().numpy().view(np.uint64), oracle.scan(a, oracle.UINT, oracle.ULONG))
+    for b in (b_in, b_out, b_carry, b_total):
+        b.destroy()
+    s.destroy()
+
+
+def test_scan_errors(clo, ctx):
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloScan("nosuchscan", ctx, oracle.UINT, oracle.UINT)
+    assert ei.value.code == clo.CLO_ERROR_IMPL_NOT_FOUND
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloScan("blelloch", ctx, oracle.UINT, oracle.UINT, options="foo=1")
+    assert ei.value.code == clo.CLO_ERROR_ARGS

@@ -1,0 +1,224 @@
+"""GPU parity: clo_sort (onesweep radix, bitonic network, gselect, pairs, partition)
+vs the CPU oracle, through the C-ABI.  Bit-exact, stable order included."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+RADIX_SIZES = [1, 2, 3, 100, 4096, 8191, 8192, 8193, 65536, 100003, (1 << 20) + 5]
+
+
+def _rand(rng, ctype, n):
+    dt = oracle.NP_TYPES[ctype]
+    if np.issubdtype(dt, np.integer):
+        info = np.iinfo(dt)
+        return rng.integers(info.min, info.max, size=n, dtype=dt, endpoint=True)
+    return ((rng.random(n) - 0.5) * 2000).astype(dt)
+
+
+@pytest.mark.parametrize("n", RADIX_SIZES)
+@pytest.mark.parametrize("et", [oracle.UINT, oracle.ULONG, oracle.UCHAR, oracle.USHORT, oracle.INT, oracle.LONG])
+def test_satradix_keys(clo, ctx, queue, et, n):
+    rng = np.random.default_rng(n + 13 * et)
+    a = _rand(rng, et, n)
+    s = clo.CloSort("satradix", ctx, et)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    want = oracle.sort_satradix(a, et, radix=16, lws=64)
+    assert np.array_equal(got, want)
+    # raw-bit ascending order == numpy sort of the unsigned view
+    u = a.view(np.dtype("u%d" % a.dtype.itemsize))
+    assert np.array_equal(got.view(u.dtype), np.sort(u))
+
+
+@pytest.mark.parametrize("opts", ["radix=2", "radix=4", "radix=256", "radix=16,scan=blelloch", "radix=32"])
+def test_satradix_radix_option_results(clo, ctx, queue, opts):
+    a = oracle.sort_input(0, oracle.UINT, 1 << 14)
+    s = clo.CloSort("satradix", ctx, oracle.UINT, options=opts)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    radix = int(opts.split(",")[0].split("=")[1])
+    want = oracle.sort_satradix(a, oracle.UINT, radix=radix, lws=256)
+    assert np.array_equal(got, want)
+
+
+def test_satradix_skewed_and_constant(clo, ctx, queue):
+    rng = np.random.default_rng(5)
+    n = (1 << 18) + 77
+    for a in (np.zeros(n, np.uint32), np.full(n, 0xFFFFFFFF, np.uint32),
+              (rng.zipf(1.3, n) % 1000).astype(np.uint32), np.arange(n, dtype=np.uint32)[::-1].copy()):
+        s = clo.CloSort("satradix", ctx, oracle.UINT)
+        got = s.with_host_data(a, queue)
+        s.destroy()
+        assert np.array_equal(got, np.sort(a))
+
+
+@pytest.mark.parametrize("get_key,shift,mask,kt", [("((x) >> 32)", 32, None, oracle.UINT),
+                                                   ("((x) & 0xFFFF)", 0, 0xFFFF, oracle.UINT),
+                                                   ("(((x) >> 8) & 0xFF)", 8, 0xFF, oracle.UCHAR)])
+def test_satradix_packed_key_value_is_stable(clo, ctx, queue, get_key, shift, mask, kt):
+    """elem = ulong packed (key | payload); equal keys must keep their input order."""
+    rng = np.random.default_rng(11)
+    n = 70001
+    a = rng.integers(0, 1 << 63, size=n, dtype=np.uint64)
+    a = (a & ~np.uint64(0xFFFF00000000)) | (rng.integers(0, 50, size=n).astype(np.uint64) << np.uint64(32))
+    s = clo.CloSort("satradix", ctx, oracle.ULONG, key_type=kt, get_key=get_key)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    want = oracle.sort_satradix(a, oracle.ULONG, radix=16, lws=64, key_type=kt, shift=shift, mask=mask)
+    assert np.array_equal(got, want)
+
+
+def test_satradix_device_data_out_of_place_and_reuse(clo, ctx, queue):
+    import torch
+    n = (1 << 20) + 999
+    a = oracle.sort_input(1, oracle.UINT, n)
+    t_in = torch.from_numpy(a.view(np.int32)).cuda()
+    t_out = torch.empty_like(t_in)
+    torch.cuda.synchronize()
+    b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+    s = clo.CloSort("satradix", ctx, oracle.UINT)
+    s.with_device_data(queue, b_in, b_out, n)
+    queue.finish()
+    assert np.array_equal(t_in.cpu().numpy().view(np.uint32), a), "input buffer was modified"
+    assert np.array_equal(t_out.cpu().numpy().view(np.uint32), np.sort(a))
+    for _ in range(2):  # in place, same sorter object twice
+        t_in.copy_(torch.from_numpy(a.view(np.int32)))
+        torch.cuda.synchronize()
+        s.with_device_data(queue, b_in, None, n)
+        queue.finish()
+        assert np.array_equal(t_in.cpu().numpy().view(np.uint32), np.sort(a))
+    b_in.destroy(); b_out.destroy(); s.destroy()
+
+
+@pytest.mark.parametrize("kt,n", [(oracle.UINT, 100003), (oracle.ULONG, 100003), (oracle.UINT, (1 << 20) + 1),
+                                  (oracle.ULONG, 1 << 20)])
+def test_sort_pairs_stable(clo, ctx, queue, kt, n):
+    import torch
+    rng = np.random.default_rng(n + kt)
+    dt = oracle.NP_TYPES[kt]
+    keys = rng.integers(0, 1000, size=n).astype(dt)            # many duplicates
+    keys[::7] = rng.integers(0, np.iinfo(dt).max, size=keys[::7].size, dtype=dt)
+    payload = np.arange(n, dtype=np.uint32)
+    tk = torch.from_numpy(keys.view(np.int32 if kt == oracle.UINT else np.int64)).cuda()
+    tp = torch.from_numpy(payload.view(np.int32)).cuda()
+    torch.cuda.synchronize()
+    bk, bp = clo.Buffer.wrap_tensor(ctx, tk), clo.Buffer.wrap_tensor(ctx, tp)
+    s = clo.CloSort("satradix", ctx, kt)
+    s.pairs_with_device_data(queue, bk, bp, n)
+    queue.finish()
+    wk, wp = oracle.sort_pairs(keys, payload, kt)
+    assert np.array_equal(tk.cpu().numpy().view(dt), wk)
+    assert np.array_equal(tp.cpu().numpy().view(np.uint32), wp)
+    bk.destroy(); bp.destroy(); s.destroy()
+
+
+@pytest.mark.parametrize("alg", ["sbitonic", "abitonic"])
+@pytest.mark.parametrize("n", [2, 4, 64, 1024, 4096, 8192, 1 << 16, 1 << 20])
+def test_bitonic_power_of_two(clo, ctx, queue, alg, n):
+    a = oracle.sort_input(0, oracle.UINT, n)
+    s = clo.CloSort(alg, ctx, oracle.UINT)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    assert np.array_equal(got, oracle.sort_bitonic(a, oracle.UINT))
+
+
+@pytest.mark.parametrize("et", [oracle.CHAR, oracle.UCHAR, oracle.SHORT, oracle.USHORT, oracle.INT, oracle.LONG,
+                                oracle.ULONG, oracle.FLOAT, oracle.DOUBLE])
+@pytest.mark.parametrize("desc", [False, True])
+def test_bitonic_types_and_compare(clo, ctx, queue, et, desc):
+    rng = np.random.default_rng(et)
+    a = _rand(rng, et, 1 << 13)
+    s = clo.CloSort("sbitonic", ctx, et, compare="((a) < (b))" if desc else None)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    want = oracle.sort_bitonic(a, et, descending=desc)
+    assert np.array_equal(got.view(np.uint8), want.view(np.uint8))
+    ref = np.sort(a)[::-1] if desc else np.sort(a)
+    assert np.array_equal(got, ref)
+
+
+def test_bitonic_network_with_get_key_is_bit_exact(clo, ctx, queue):
+    """unstable network + non-trivial key: only the canonical network reproduces this."""
+    rng = np.random.default_rng(3)
+    n = 1 << 14
+    a = rng.integers(0, 1 << 62, size=n, dtype=np.uint64)
+    a = (a & ~np.uint64(0xFF)) | rng.integers(0, 4, size=n).astype(np.uint64)
+    s = clo.CloSort("abitonic", ctx, oracle.ULONG, key_type=oracle.UCHAR, get_key="((x) & 0xFF)")
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    want = oracle.sort_bitonic(a, oracle.ULONG, key_type=oracle.UCHAR, mask=0xFF)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n", [3, 100, 5000, 4097, 100003])
+def test_bitonic_any_n(clo, ctx, queue, n):
+    a = oracle.sort_input(2, oracle.UINT, n)
+    s = clo.CloSort("sbitonic", ctx, oracle.UINT)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    assert np.array_equal(got, np.sort(a))
+
+
+@pytest.mark.parametrize("n", [1, 17, 256, 1000, 5000])
+def test_gselect_stable_rank(clo, ctx, queue, n):
+    rng = np.random.default_rng(n)
+    a = (rng.integers(0, 1 << 62, size=n, dtype=np.uint64) & ~np.uint64(0xFF)) | \
+        rng.integers(0, 8, size=n).astype(np.uint64)
+    s = clo.CloSort("gselect", ctx, oracle.ULONG, key_type=oracle.UCHAR, get_key="((x) & 0xFF)")
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    assert np.array_equal(got, oracle.sort_gselect(a, oracle.ULONG, key_type=oracle.UCHAR, mask=0xFF))
+
+
+def test_partition_by_splitters(clo, ctx, queue):
+    """sample-sort building block: stable multi-way partition with (key, index) splitters."""
+    import torch
+    rng = np.random.default_rng(9)
+    n, P, g0 = 300001, 8, 10_000_000
+    keys = rng.integers(0, 50, size=n).astype(np.uint32)      # heavy duplication
+    payload = np.arange(n, dtype=np.uint32)
+    sk = np.array([5, 5, 20, 20, 20, 33, 49], dtype=np.uint32)
+    si = np.array([g0 + 10, g0 + 200000, g0 + 5, g0 + 100000, g0 + 250000, 0, g0 + n], dtype=np.uint64)
+    g = g0 + np.arange(n, dtype=np.uint64)
+    bucket = np.zeros(n, dtype=np.int64)
+    for k_, i_ in zip(sk, si):
+        bucket += ((k_ < keys) | ((k_ == keys) & (i_ <= g))).astype(np.int64)
+    order = np.argsort(bucket, kind="stable")
+    t = {name: torch.from_numpy(arr).cuda() for name, arr in
+         dict(k=keys.view(np.int32), p=payload.view(np.int32), sk=sk.view(np.int32), si=si.view(np.int64)).items()}
+    t["ko"], t["po"] = torch.empty_like(t["k"]), torch.empty_like(t["p"])
+    t["cnt"] = torch.zeros(P, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    b = {name: clo.Buffer.wrap_tensor(ctx, x) for name, x in t.items()}
+    s = clo.CloSort("satradix", ctx, oracle.UINT)
+    s.partition_with_device_data(queue, b["k"], b["p"], b["ko"], b["po"], n, g0, b["sk"], b["si"], P, b["cnt"])
+    queue.finish()
+    assert np.array_equal(t["cnt"].cpu().numpy(), np.bincount(bucket, minlength=P))
+    assert np.array_equal(t["ko"].cpu().numpy().view(np.uint32), keys[order])
+    assert np.array_equal(t["po"].cpu().numpy().view(np.uint32), payload[order])
+    for x in b.values():
+        x.destroy()
+    s.destroy()
+
+
+def test_sort_errors(clo, ctx):
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloSort("quicksort", ctx, oracle.UINT)
+    assert ei.value.code == clo.CLO_ERROR_IMPL_NOT_FOUND
+    for kw in (dict(options="radix=3"), dict(options="bogus=1"), dict(options="radix")):
+        with pytest.raises(clo.CloError) as ei:
+            clo.CloSort("satradix", ctx, oracle.UINT, **kw)
+        assert ei.value.code == clo.CLO_ERROR_ARGS
+    for kw in (dict(options="minps=5"), dict(options="minps=3,maxps=2"), dict(options="zzz=1")):
+        with pytest.raises(clo.CloError) as ei:
+            clo.CloSort("abitonic", ctx, oracle.UINT, **kw)
+        assert ei.value.code == clo.CLO_ERROR_ARGS
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloSort("sbitonic", ctx, oracle.UINT, compare="((a) >= (b))")
+    assert ei.value.code == clo.CLO_ERROR_ARGS
+    s = clo.CloSort("satradix", ctx, oracle.UINT)
+    assert s.kernel_names() == ["clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep"]
+    s.destroy()

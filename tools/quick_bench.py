@@ -1,0 +1,166 @@
+"""tools/quick_bench.py -- device-timed throughput of the three hot kernels at the
+BASELINE.json sizes (development aid; bench.py is the contract).  CUDA events on the
+stream the library launches on (the torch current stream, wrapped as a CCLQueue)."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import cl_ops_b200 as clo  # noqa: E402
+
+
+def timed(fn, iters, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        times.append(a.elapsed_time(b))
+    return float(np.median(times)), float(np.min(times))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log2n-sort", type=int, default=28)
+    ap.add_argument("--log2n-scan", type=int, default=30)
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--what", default="sort,sort64,pairs,scan,scanf,rng,bitonic")
+    args = ap.parse_args()
+    what = args.what.split(",")
+    peak = 6542.1
+    try:
+        peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    ctx = clo.Context()
+    q = clo.Queue(ctx, stream=torch.cuda.current_stream().cuda_stream)
+    res = {}
+
+    if "sort" in what:
+        n = 1 << args.log2n_sort
+        t_in = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
+        t_out = torch.empty_like(t_in)
+        b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+        s = clo.CloSort("satradix", ctx, clo.UINT)
+        med, best = timed(lambda: s.with_device_data(q, b_in, b_out, n), args.iters)
+        chk = t_out.view(torch.int32)
+        u = (chk.to(torch.int64) & 0xFFFFFFFF)
+        ok = bool((u[1:] >= u[:-1]).all().item())
+        res["sort_u32"] = dict(n=n, ms=med, ms_best=best, gkeys=n / med / 1e6, gbs=36.0 * n / med / 1e6,
+                               frac=36.0 * n / med / 1e6 / peak, sorted=ok)
+        print(json.dumps({"sort_u32": res["sort_u32"]}), flush=True)
+        b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out, chk, u
+        torch.cuda.empty_cache()
+
+    if "sort64" in what:
+        n = 1 << (args.log2n_sort - 1)
+        t_in = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda")
+        t_out = torch.empty_like(t_in)
+        b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+        s = clo.CloSort("satradix", ctx, clo.ULONG)
+        med, best = timed(lambda: s.with_device_data(q, b_in, b_out, n), args.iters)
+        res["sort_u64"] = dict(n=n, ms=med, gkeys=n / med / 1e6, gbs=136.0 * n / med / 1e6,
+                               frac=136.0 * n / med / 1e6 / peak)
+        print(json.dumps({"sort_u64": res["sort_u64"]}), flush=True)
+        b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out
+        torch.cuda.empty_cache()
+
+    if "pairs" in what:
+        n = 1 << (args.log2n_sort - 1)
+        k0 = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda")
+        tk = torch.empty_like(k0)
+        tp = torch.empty(n, dtype=torch.int32, device="cuda")
+        bk, bp = clo.Buffer.wrap_tensor(ctx, tk), clo.Buffer.wrap_tensor(ctx, tp)
+        s = clo.CloSort("satradix", ctx, clo.ULONG)
+
+        def run():
+            tk.copy_(k0)
+            tp.copy_(torch.arange(n, dtype=torch.int32, device="cuda"))
+            s.pairs_with_device_data(q, bk, bp, n)
+        med_all, _ = timed(run, max(3, args.iters // 2))
+
+        def fill():
+            tk.copy_(k0)
+            tp.copy_(torch.arange(n, dtype=torch.int32, device="cuda"))
+        med_fill, _ = timed(fill, max(3, args.iters // 2))
+        med = med_all - med_fill
+        res["pairs_u64_u32"] = dict(n=n, ms=med, gpairs=n / med / 1e6, gbs=200.0 * n / med / 1e6,
+                                    frac=200.0 * n / med / 1e6 / peak)
+        print(json.dumps({"pairs_u64_u32": res["pairs_u64_u32"]}), flush=True)
+        bk.destroy(); bp.destroy(); s.destroy(); del k0, tk, tp
+        torch.cuda.empty_cache()
+
+    for name, et, st, tdt, bytes_per in (("scan", clo.UINT, clo.UINT, torch.int32, 8),
+                                         ("scan64", clo.UINT, clo.ULONG, torch.int32, 12),
+                                         ("scanf", clo.FLOAT, clo.FLOAT, torch.float32, 8)):
+        if name not in what and not (name == "scan64" and "scan" in what):
+            continue
+        n = 1 << args.log2n_scan
+        if tdt == torch.float32:
+            t_in = torch.rand(n, dtype=tdt, device="cuda")
+        else:
+            t_in = torch.randint(0, 128, (n,), dtype=tdt, device="cuda")
+        t_out = torch.empty(n, dtype=torch.int64 if st == clo.ULONG else tdt, device="cuda")
+        b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+        s = clo.CloScan("blelloch", ctx, et, st)
+        med, best = timed(lambda: s.with_device_data(q, b_in, b_out, n), args.iters)
+        if tdt != torch.float32:
+            # spot check: last element equals the sum of all but the last input
+            want = int(t_in[:-1].to(torch.int64).sum().item())
+            got = int(t_out[-1].item())
+            if st == clo.UINT:
+                want &= 0xFFFFFFFF
+                got &= 0xFFFFFFFF
+            ok = want == got
+        else:
+            ok = None
+        res[name] = dict(n=n, ms=med, ms_best=best, gelem=n / med / 1e6, gbs=bytes_per * n / med / 1e6,
+                         frac=bytes_per * n / med / 1e6 / peak, check=ok)
+        print(json.dumps({name: res[name]}), flush=True)
+        b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out
+        torch.cuda.empty_cache()
+
+    if "rng" in what:
+        G, runs = 1 << 22, 256
+        t_out = torch.empty(G * runs, dtype=torch.int32, device="cuda")
+        b_out = clo.Buffer.wrap_tensor(ctx, t_out)
+        for rng in ("lcg", "xorshift64", "xorshift128", "mwc64x", "parkmiller", "tauslcg"):
+            r = clo.CloRng(rng, ctx, clo.SEED_DEV_GID, None, G, 0, "KNUTH(x)", q)
+            med, best = timed(lambda: r.generate(q, b_out, runs), max(3, args.iters // 2))
+            res["rng_" + rng] = dict(words=G * runs, ms=med, gwords=G * runs / med / 1e6,
+                                     gbs=4.0 * G * runs / med / 1e6, frac=4.0 * G * runs / med / 1e6 / peak)
+            print(json.dumps({"rng_" + rng: res["rng_" + rng]}), flush=True)
+            r.destroy()
+        b_out.destroy(); del t_out
+        torch.cuda.empty_cache()
+
+    if "bitonic" in what:
+        n = 1 << 20
+        a0 = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
+        t = torch.empty_like(a0)
+        b = clo.Buffer.wrap_tensor(ctx, t)
+        s = clo.CloSort("sbitonic", ctx, clo.UINT)
+
+        def run():
+            t.copy_(a0)
+            s.with_device_data(q, b, None, n)
+        med, best = timed(run, args.iters)
+        res["sbitonic_2^20"] = dict(n=n, ms=med, mkeys=n / med / 1e3)
+        print(json.dumps({"sbitonic_2^20": res["sbitonic_2^20"]}), flush=True)
+        b.destroy(); s.destroy()
+
+    print(json.dumps(res))
+    q.destroy(); ctx.destroy()
+
+
+if __name__ == "__main__":
+    main()
