@@ -34,6 +34,7 @@ const int RADIX_BITS = 8;
 const int RADIX = 1 << RADIX_BITS;
 const int MAX_PASSES = 8;
 const unsigned SPIN_LIMIT = 1u << 26;
+const int LB_BATCH = 4;
 
 struct PassCfg {
 	int passes;
@@ -131,14 +132,21 @@ clo_radix_scan_bins(const u64* __restrict__ ghist, u64* __restrict__ bins_base) 
 
 /* -------------------------------------------------------------- onesweep */
 
-/* lanes of the warp whose digit equals mine (8 ballots) */
+/* lanes of the warp whose digit equals mine: one ballot per digit bit, 4 SASS
+ * instructions per bit (test, vote, conditional invert, and) */
 __device__ __forceinline__ u32 match_digit_ballot(u32 d) {
 	u32 peers = 0xffffffffu;
 #pragma unroll
 	for (int b = 0; b < RADIX_BITS; ++b) {
-		const bool bit = (d >> b) & 1u;
-		const u32 m = __ballot_sync(0xffffffffu, bit);
-		peers &= bit ? m : ~m;
+		asm("{\n\t"
+			".reg .pred p;\n\t"
+			".reg .b32 m, t;\n\t"
+			"and.b32 t, %1, %2;\n\t"
+			"setp.ne.u32 p, t, 0;\n\t"
+			"vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
+			"@!p not.b32 m, m;\n\t"
+			"and.b32 %0, %0, m;\n\t"
+			"}" : "+r"(peers) : "r"(d), "r"(1u << b));
 	}
 	return peers;
 }
@@ -160,7 +168,7 @@ struct SplitterArgs {
 
 template <typename ElemT, bool HAS_VAL, bool IDENTITY, bool PARTITION, typename LbT,
 	int THREADS, int IPT, int MATCH_HW>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS >= 384 ? 2 : 4))
 clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
 		LbT* __restrict__ lookback, u32* __restrict__ ticket, const u64* __restrict__ bins_base,
@@ -172,8 +180,8 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	u32* whist = reinterpret_cast<u32*>(smem_raw);                         /* [WARPS][RADIX] */
 	u32* s_dstart = whist + WARPS * RADIX;                                 /* [RADIX] */
-	u64* s_goff = reinterpret_cast<u64*>(s_dstart + RADIX);                /* [RADIX] */
-	u32* s_misc = reinterpret_cast<u32*>(s_goff + RADIX);                  /* [16]: tile, warp sums */
+	LbT* s_goff = reinterpret_cast<LbT*>(s_dstart + RADIX);                /* [RADIX] (u64-sized slot) */
+	u32* s_misc = s_dstart + RADIX + 2 * RADIX;                            /* [16]: tile, warp sums */
 	ElemT* skeys = reinterpret_cast<ElemT*>(s_misc + 16);                  /* [TILE] */
 	u32* svals = reinterpret_cast<u32*>(skeys + TILE);                     /* [TILE] if HAS_VAL */
 
@@ -276,7 +284,11 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			u32 off = 0;
 #pragma unroll
 			for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[1 + w];
-			s_dstart[tid] = off + incl - count;
+			const u32 ds = off + incl - count;
+			s_dstart[tid] = ds;
+			/* fold the digit start into the per-warp offsets: one table lookup when staging */
+#pragma unroll
+			for (int w = 0; w < WARPS; ++w) whist[w * RADIX + tid] += ds;
 		}
 	}
 	if (tid < RADIX) {
@@ -284,20 +296,31 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		if (tile > 0) {
 			long long p = (long long) tile - 1;
 			unsigned spins = 0;
-			for (;;) {
-				const LbT w = ld_relaxed(lookback + (size_t) p * RADIX + tid);
-				const LbT f = w & Lb<LbT>::FLAGS;
-				if (f == 0) {
-					if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
-					continue;
+			bool done = false;
+			while (!done) {
+				/* LB_BATCH predecessor words in flight at once; consumed nearest first */
+				LbT w[LB_BATCH];
+#pragma unroll
+				for (int k = 0; k < LB_BATCH; ++k)
+					w[k] = (p - k >= 0) ? ld_relaxed(lookback + (size_t) (p - k) * RADIX + tid) : (LbT) Lb<LbT>::PREFIX;
+#pragma unroll
+				for (int k = 0; k < LB_BATCH; ++k) {
+					if (!done) {
+						const LbT f = w[k] & Lb<LbT>::FLAGS;
+						if (f == 0) {            /* not published yet: retry from here */
+							if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); done = true; }
+							break;
+						}
+						excl += w[k] & Lb<LbT>::VAL;
+						--p;
+						if (f == Lb<LbT>::PREFIX) done = true;
+					}
 				}
-				excl += w & Lb<LbT>::VAL;
-				if (f == Lb<LbT>::PREFIX) break;
-				--p;
 			}
 			st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | ((excl + count) & Lb<LbT>::VAL)));
 		}
-		s_goff[tid] = bins_base[tid] + (u64) excl - (u64) s_dstart[tid];
+		/* modular arithmetic in LbT: the final index goff[d] + j is < n */
+		s_goff[tid] = (LbT) bins_base[tid] + excl - (LbT) s_dstart[tid];
 	}
 	__syncthreads();
 
@@ -307,7 +330,7 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		const u32 local = wbase + i * 32u;
 		if (full || local < tile_count) {
 			const u32 d = digit_of(key[i], local);
-			const u32 p = s_dstart[d] + wh[d] + pos[i];
+			const u32 p = wh[d] + pos[i];
 			skeys[p] = key[i];
 			if (HAS_VAL) svals[p] = val[i];
 			if (PARTITION) pos[i] = p;
@@ -323,7 +346,7 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			if (full || j < tile_count) {
 				const ElemT k = skeys[j];
 				const u32 d = radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
-				const u64 o = s_goff[d] + j;
+				const LbT o = s_goff[d] + (LbT) j;
 				out[o] = k;
 				if (HAS_VAL) vout[o] = svals[j];
 			}
@@ -338,7 +361,7 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 				u32 d = 0;
 #pragma unroll
 				for (int s = 1; s < 16; ++s) if (s <= (int) sp.count && j >= s_dstart[s]) d = s;
-				const u64 o = s_goff[d] + j;
+				const LbT o = s_goff[d] + (LbT) j;
 				out[o] = skeys[j];
 				if (HAS_VAL) vout[o] = svals[j];
 			}
@@ -367,12 +390,15 @@ struct CloRadixState {
 	CloScratch aux_vals;
 	CloScratch work;         /* [err | ghist | bins_base | tickets | lookback...] */
 	int match_hw = 0;
+	int cfg = 0;
 };
 
 CloRadixState* clo_radix_state_new() {
 	CloRadixState* st = new CloRadixState();
 	const char* e = getenv("CLO_RADIX_MATCH_HW");
 	st->match_hw = (e && *e == '1') ? 1 : 0;
+	const char* c = getenv("CLO_RADIX_CFG");
+	st->cfg = (c && *c) ? atoi(c) : 0;
 	return st;
 }
 
@@ -416,12 +442,10 @@ cudaError_t prepare_work(CloRadixState* st, size_t tiles, int passes, size_t lb_
 	return cudaMemsetAsync(base, 0, L.zero_bytes, stream);
 }
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int MATCH_HW>
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int MATCH_HW, int THREADS, int IPT>
 cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n,
 		LbT* lookback, u32* ticket, const u64* bins, u32 start_bit, u32 dmask, const CloKeySpec& ks,
 		int* err, cudaStream_t stream) {
-	constexpr int THREADS = TileCfg<ElemT, HAS_VAL>::THREADS;
-	constexpr int IPT = TileCfg<ElemT, HAS_VAL>::IPT;
 	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT>();
 	auto kern = clo_radix_onesweep<ElemT, HAS_VAL, IDENTITY, false, LbT, THREADS, IPT, MATCH_HW>;
 	static bool configured[64] = {};
@@ -440,11 +464,9 @@ cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vo
 	return cudaGetLastError();
 }
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY>
-cudaError_t radix_sort_typed(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, int THREADS, int IPT>
+cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
 		const ElemT* src, ElemT* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
-	constexpr int THREADS = TileCfg<ElemT, HAS_VAL>::THREADS;
-	constexpr int IPT = TileCfg<ElemT, HAS_VAL>::IPT;
 	constexpr size_t TILE = (size_t) THREADS * IPT;
 	cudaError_t e;
 	PassCfg cfg;
@@ -496,18 +518,39 @@ cudaError_t radix_sort_typed(CloRadixState* st, int sm_count, const CloKeySpec& 
 		if (wide) {
 			u64* lb = (u64*) L.lookback + (size_t) p * tiles * RADIX;
 			e = st->match_hw
-				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 1>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
-				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
+				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		} else {
 			u32* lb = (u32*) L.lookback + (size_t) p * tiles * RADIX;
 			e = st->match_hw
-				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 1>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
-				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
+				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		}
 		if (e != cudaSuccess) return e;
 		cur = nxt; vcur = vnxt;
 	}
 	return cudaSuccess;
+}
+
+template <typename ElemT, bool HAS_VAL, bool IDENTITY>
+cudaError_t radix_sort_typed(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
+		const ElemT* src, ElemT* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
+	return radix_sort_cfg<ElemT, HAS_VAL, IDENTITY, TileCfg<ElemT, HAS_VAL>::THREADS, TileCfg<ElemT, HAS_VAL>::IPT>(
+		st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+}
+
+/* tuning variants for the headline case (u32 keys only, identity key), chosen with
+ * CLO_RADIX_CFG; the default is TileCfg */
+template <>
+cudaError_t radix_sort_typed<u32, false, true>(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
+		const u32* src, u32* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
+	switch (st->cfg) {
+	case 1: return radix_sort_cfg<u32, false, true, 256, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 2: return radix_sort_cfg<u32, false, true, 384, 18>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 3: return radix_sort_cfg<u32, false, true, 256, 24>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 4: return radix_sort_cfg<u32, false, true, 512, 12>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	default: return radix_sort_cfg<u32, false, true, 512, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	}
 }
 
 template <typename ElemT>

@@ -58,9 +58,12 @@ const unsigned SPIN_LIMIT = 1u << 26;
 
 /* ------------------------------------------------------------------ kernel */
 
+/* Persistent, software-pipelined single-pass scan.  A CTA repeatedly takes a tile
+ * ticket; the loads of its NEXT tile are issued before it waits on the look-back
+ * of the current one, so HBM stays busy while prefixes propagate. */
 template <typename ElemT, typename SumT, int THREADS, int VPT>
 __global__ void __launch_bounds__(THREADS)
-clo_scan_lookback(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n,
+clo_scan_lookback(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 num_tiles,
 		u64* __restrict__ desc, u32* __restrict__ ticket, u32 ticket_base, u32 epoch,
 		const SumT* __restrict__ carry_in, int vec_in, int vec_out, int* __restrict__ err_flag) {
 	typedef typename AccOf<SumT>::type AccT;
@@ -71,148 +74,165 @@ clo_scan_lookback(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n
 	/* output chunk: at most 16 bytes per store */
 	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
 
-	__shared__ u32 s_tile;
+	__shared__ u32 s_next;
 	__shared__ AccT s_warp[WARPS];
 	__shared__ AccT s_prefix;
 
-	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u) - ticket_base;
-	__syncthreads();
-	const u32 tile = s_tile;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const size_t tile_base = (size_t) tile * TILE;
-	const bool full = tile_base + TILE <= n;
+	const u32 lane_off = ((u32) (warp * VPT) * 32u + lane) * EPV;   /* + j*32*EPV per row */
 
-	/* ---- load: warp-striped vectors (row j of warp w is 32*EPV contiguous elements) */
-	AccT v[VPT][EPV];
+	auto load_tile = [&](u32 t, ElemT (&e)[VPT][EPV]) {
+		const size_t tile_base = (size_t) t * TILE;
+		const bool full = tile_base + TILE <= n;
 #pragma unroll
-	for (int j = 0; j < VPT; ++j) {
-		const size_t idx = tile_base + ((size_t) (warp * VPT + j) * 32 + lane) * EPV;
-		ElemT e[EPV];
-		if (vec_in && (full || idx + EPV <= n)) {
-			load_vec_cs<ElemT, EPV>(in + idx, e);
-		} else {
+		for (int j = 0; j < VPT; ++j) {
+			const size_t idx = tile_base + lane_off + (size_t) j * 32 * EPV;
+			if (vec_in && (full || idx + EPV <= n)) {
+				load_vec_cs<ElemT, EPV>(in + idx, e[j]);
+			} else {
 #pragma unroll
-			for (int c = 0; c < EPV; ++c) e[c] = (idx + c < n) ? in[idx + c] : ElemT(0);
+				for (int c = 0; c < EPV; ++c) e[j][c] = (idx + c < n) ? in[idx + c] : ElemT(0);
+			}
 		}
-#pragma unroll
-		for (int c = 0; c < EPV; ++c) v[j][c] = to_acc<ElemT, SumT, AccT>(e[c]);
-	}
+	};
 
-	/* ---- thread: inclusive scan inside each vector; warp: scan of vector sums per row */
-	AccT base[VPT];
-	AccT warp_total = AccT(0);
-#pragma unroll
-	for (int j = 0; j < VPT; ++j) {
-#pragma unroll
-		for (int c = 1; c < EPV; ++c) v[j][c] += v[j][c - 1];
-		AccT incl = warp_inclusive_scan<AccT>(v[j][EPV - 1], lane);
-		AccT excl = __shfl_up_sync(0xffffffffu, incl, 1);
-		if (lane == 0) excl = AccT(0);
-		AccT row_total = __shfl_sync(0xffffffffu, incl, 31);
-		base[j] = warp_total + excl;
-		warp_total += row_total;
-	}
-
-	/* ---- block: offsets of the warps, tile aggregate */
-	if (lane == 0) s_warp[warp] = warp_total;
+	if (threadIdx.x == 0) s_next = atomicAdd(ticket, 1u) - ticket_base;
 	__syncthreads();
-	AccT warp_off = AccT(0), aggregate = AccT(0);
-#pragma unroll
-	for (int w = 0; w < WARPS; ++w) {
-		AccT t = s_warp[w];
-		if (w < warp) warp_off += t;
-		aggregate += t;
-	}
+	u32 tile = s_next;
+	__syncthreads();
+	if (tile >= num_tiles) return;
+	const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
+	const u64 fl_agg = ((u64) ((epoch << 2) | ST_AGG)) << 32;
+	const u64 fl_pre = ((u64) ((epoch << 2) | ST_PREFIX)) << 32;
 
-	/* ---- decoupled look-back (warp 0; lane i inspects tile-1-i) */
-	if (warp == 0) {
-		const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
-		const u64 fl_agg = ((u64) ((epoch << 2) | ST_AGG)) << 32;
-		const u64 fl_pre = ((u64) ((epoch << 2) | ST_PREFIX)) << 32;
+	ElemT cur[VPT][EPV];
+	load_tile(tile, cur);
+
+	for (;;) {
+		/* ticket of the next tile: issued now, consumed after the local scan */
+		u32 tk = 0;
+		if (threadIdx.x == 0) tk = atomicAdd(ticket, 1u) - ticket_base;
+
+		/* ---- thread: inclusive scan inside each vector; warp: scan of vector sums per row */
+		AccT v[VPT][EPV];
+		AccT base[VPT];
+		AccT warp_total = AccT(0);
+#pragma unroll
+		for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) v[j][c] = to_acc<ElemT, SumT, AccT>(cur[j][c]);
+#pragma unroll
+			for (int c = 1; c < EPV; ++c) v[j][c] += v[j][c - 1];
+			AccT incl = warp_inclusive_scan<AccT>(v[j][EPV - 1], lane);
+			AccT excl = __shfl_up_sync(0xffffffffu, incl, 1);
+			if (lane == 0) excl = AccT(0);
+			AccT row_total = __shfl_sync(0xffffffffu, incl, 31);
+			base[j] = warp_total + excl;
+			warp_total += row_total;
+		}
+
+		/* ---- block: offsets of the warps, tile aggregate */
+		if (lane == 0) s_warp[warp] = warp_total;
+		if (threadIdx.x == 0) s_next = tk;
+		__syncthreads();
+		AccT warp_off = AccT(0), aggregate = AccT(0);
+#pragma unroll
+		for (int w = 0; w < WARPS; ++w) {
+			AccT t = s_warp[w];
+			if (w < warp) warp_off += t;
+			aggregate += t;
+		}
+		const u32 next_tile = s_next;
 		u64* mine = desc + (size_t) tile * AW::N;
-		AccT exclusive = carry;
-		if (tile == 0) {
-			if (lane == 0) {
-				u32 w[AW::N];
-				AW::pack(carry + aggregate, w);
+		if (threadIdx.x == 0) {
+			/* publish as early as possible: tile 0 knows its inclusive prefix already */
+			u32 w[AW::N];
+			AW::pack(tile == 0 ? (AccT) (carry + aggregate) : aggregate, w);
 #pragma unroll
-				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
-			}
-		} else {
-			if (lane == 0) {
-				u32 w[AW::N];
-				AW::pack(aggregate, w);
-#pragma unroll
-				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_agg | w[k]);
-			}
-			exclusive = AccT(0);
-			long long look = (long long) tile - 1;
-			unsigned spins = 0;
-			bool done = false;
-			while (!done) {
-				const long long idx = look - lane;
-				u32 state = ST_PREFIX;  /* lanes before tile 0 act as an empty prefix */
-				AccT val = AccT(0);
-				if (idx >= 0) {
-					const u64* p = desc + (size_t) idx * AW::N;
-					for (;;) {
-						u32 w[AW::N];
-						u32 st = 0;
-						bool ok = true;
-#pragma unroll
-						for (int k = 0; k < AW::N; ++k) {
-							const u64 x = ld_relaxed(p + k);
-							const u32 f = (u32) (x >> 32);
-							w[k] = (u32) x;
-							if ((f >> 2) != epoch || (f & 3u) == 0) ok = false;
-							if (k == 0) st = f & 3u; else if ((f & 3u) != st) ok = false;
-						}
-						if (ok) { state = st; val = AW::unpack(w); break; }
-						if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
-					}
-				} else if (idx == -1) {
-					val = carry;   /* the scan's carry-in sits "before tile 0" */
-				}
-				const u32 pmask = __ballot_sync(0xffffffffu, state == ST_PREFIX);
-				const int first = pmask ? (__ffs(pmask) - 1) : 32;
-				AccT contrib = (lane <= first) ? val : AccT(0);
-				exclusive += warp_reduce_sum<AccT>(contrib);
-				done = (pmask != 0);
-				look -= 32;
-			}
-			if (lane == 0) {
-				u32 w[AW::N];
-				AW::pack(exclusive + aggregate, w);
-#pragma unroll
-				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
-			}
+			for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, (tile == 0 ? fl_pre : fl_agg) | w[k]);
 		}
-		if (lane == 0) s_prefix = exclusive;
-	}
-	__syncthreads();
-	const AccT tile_prefix = s_prefix + warp_off;
 
-	/* ---- store: same warp-striped layout */
+		/* ---- prefetch the next tile before waiting on predecessors */
+		const bool more = next_tile < num_tiles;
+		if (more) load_tile(next_tile, cur);
+
+		/* ---- decoupled look-back (warp 0; lane i inspects tile-1-i) */
+		if (warp == 0) {
+			AccT exclusive = carry;
+			if (tile != 0) {
+				exclusive = AccT(0);
+				long long look = (long long) tile - 1;
+				unsigned spins = 0;
+				bool done = false;
+				while (!done) {
+					const long long idx = look - lane;
+					u32 state = ST_PREFIX;  /* lanes before tile 0 act as an empty prefix */
+					AccT val = AccT(0);
+					if (idx >= 0) {
+						const u64* p = desc + (size_t) idx * AW::N;
+						for (;;) {
+							u32 w[AW::N];
+							u32 st = 0;
+							bool ok = true;
 #pragma unroll
-	for (int j = 0; j < VPT; ++j) {
-		const size_t idx = tile_base + ((size_t) (warp * VPT + j) * 32 + lane) * EPV;
-		const AccT b = tile_prefix + base[j];
-		SumT o[EPV];
-		o[0] = static_cast<SumT>(b);
+							for (int k = 0; k < AW::N; ++k) {
+								const u64 x = ld_relaxed(p + k);
+								const u32 f = (u32) (x >> 32);
+								w[k] = (u32) x;
+								if ((f >> 2) != epoch || (f & 3u) == 0) ok = false;
+								if (k == 0) st = f & 3u; else if ((f & 3u) != st) ok = false;
+							}
+							if (ok) { state = st; val = AW::unpack(w); break; }
+							if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
+						}
+					}
+					const u32 pmask = __ballot_sync(0xffffffffu, state == ST_PREFIX);
+					const int first = pmask ? (__ffs(pmask) - 1) : 32;
+					AccT contrib = (lane <= first) ? val : AccT(0);
+					exclusive += warp_reduce_sum<AccT>(contrib);
+					done = (pmask != 0);
+					look -= 32;
+				}
+				if (lane == 0) {
+					u32 w[AW::N];
+					AW::pack(exclusive + aggregate, w);
 #pragma unroll
-		for (int c = 1; c < EPV; ++c) o[c] = static_cast<SumT>(b + v[j][c - 1]);
-		if (vec_out && (full || idx + EPV <= n)) {
-#pragma unroll
-			for (int c0 = 0; c0 < EPV; c0 += OCH) {
-				SumT chunk[OCH];
-#pragma unroll
-				for (int c = 0; c < OCH; ++c) chunk[c] = o[c0 + c];
-				store_vec_cs<SumT, OCH>(out + idx + c0, chunk);
+					for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
+				}
 			}
-		} else {
-#pragma unroll
-			for (int c = 0; c < EPV; ++c) if (idx + c < n) out[idx + c] = o[c];
+			if (lane == 0) s_prefix = exclusive;
 		}
+		__syncthreads();
+		const AccT tile_prefix = s_prefix + warp_off;
+
+		/* ---- store: same warp-striped layout */
+		{
+			const size_t tile_base = (size_t) tile * TILE;
+			const bool full = tile_base + TILE <= n;
+#pragma unroll
+			for (int j = 0; j < VPT; ++j) {
+				const size_t idx = tile_base + lane_off + (size_t) j * 32 * EPV;
+				const AccT b = tile_prefix + base[j];
+				SumT o[EPV];
+				o[0] = static_cast<SumT>(b);
+#pragma unroll
+				for (int c = 1; c < EPV; ++c) o[c] = static_cast<SumT>(b + v[j][c - 1]);
+				if (vec_out && (full || idx + EPV <= n)) {
+#pragma unroll
+					for (int c0 = 0; c0 < EPV; c0 += OCH) {
+						SumT chunk[OCH];
+#pragma unroll
+						for (int c = 0; c < OCH; ++c) chunk[c] = o[c0 + c];
+						store_vec_cs<SumT, OCH>(out + idx + c0, chunk);
+					}
+				} else {
+#pragma unroll
+					for (int c = 0; c < EPV; ++c) if (idx + c < n) out[idx + c] = o[c];
+				}
+			}
+		}
+		if (!more) break;
+		tile = next_tile;
 	}
 }
 
@@ -276,7 +296,7 @@ struct ScanState {
 const size_t HDR_BYTES = 256;
 
 template <typename ElemT, typename SumT>
-cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, const void* carry, cudaStream_t stream) {
+cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) {
 	typedef typename AccOf<SumT>::type AccT;
 	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
 	constexpr size_t TILE = (size_t) SCAN_THREADS * SCAN_VPT * EPV;
@@ -301,11 +321,22 @@ cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, cons
 	const int vec_in = (reinterpret_cast<uintptr_t>(in) % (sizeof(ElemT) * EPV)) == 0;
 	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
 	const int vec_out = (reinterpret_cast<uintptr_t>(out) % (sizeof(SumT) * OCH)) == 0;
-	clo_scan_lookback<ElemT, SumT, SCAN_THREADS, SCAN_VPT><<<(unsigned) tiles, SCAN_THREADS, 0, stream>>>(
-		(const ElemT*) in, (SumT*) out, n, desc, ticket, st.ticket_base, st.epoch,
+	/* persistent grid: as many CTAs as fit on the device at once (never more than tiles) */
+	static int ctas_per_sm = 0;
+	if (!ctas_per_sm) {
+		int k = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, clo_scan_lookback<ElemT, SumT, SCAN_THREADS, SCAN_VPT>,
+				SCAN_THREADS, 0) != cudaSuccess || k < 1) k = 2;
+		ctas_per_sm = k;
+	}
+	size_t grid = (size_t) sms * ctas_per_sm;
+	if (grid > tiles) grid = tiles;
+	clo_scan_lookback<ElemT, SumT, SCAN_THREADS, SCAN_VPT><<<(unsigned) grid, SCAN_THREADS, 0, stream>>>(
+		(const ElemT*) in, (SumT*) out, n, (u32) tiles, desc, ticket, st.ticket_base, st.epoch,
 		(const SumT*) carry, vec_in, vec_out, err_flag);
 	CLO_COUNT_LAUNCH(1);
-	st.ticket_base += (u32) tiles;
+	/* every CTA draws one ticket past the end before it exits */
+	st.ticket_base += (u32) (tiles + grid);
 	(void) sizeof(AccT);
 	return cudaGetLastError();
 }
@@ -322,7 +353,7 @@ cudaError_t launch_reduce(ScanState& st, const void* in, void* total_out, size_t
 	return cudaGetLastError();
 }
 
-typedef cudaError_t (*ScanFn)(ScanState&, const void*, void*, size_t, const void*, cudaStream_t);
+typedef cudaError_t (*ScanFn)(ScanState&, const void*, void*, size_t, const void*, int, cudaStream_t);
 typedef cudaError_t (*ReduceFn)(ScanState&, const void*, void*, size_t, int, cudaStream_t);
 
 /* CloType -> C++ type (half is not an arithmetic type in OpenCL C without
@@ -443,7 +474,8 @@ static CCLEvent* scan_device(CloScan* scanner, CCLQueue* cq_exec, CCLBuffer* dat
 	ccl_event* evt = clo_queue_begin(cq_exec, "clo_scan_lookback");
 	cudaError_t rc = cudaSuccess;
 	if (numel > 0)
-		rc = scanner->fn(scanner->st, data_in->ptr, data_out->ptr, numel, carry ? carry->ptr : NULL, cq_exec->stream);
+		rc = scanner->fn(scanner->st, data_in->ptr, data_out->ptr, numel, carry ? carry->ptr : NULL,
+			clo_sm_count(cq_exec->ctx->dev.ordinal), cq_exec->stream);
 	clo_queue_end(cq_exec, evt);
 	if (clo_cuda_failed(rc, err, "clo_scan_lookback launch")) return NULL;
 	return evt;

@@ -80,7 +80,7 @@ def generate(ref):
 
     # ---------------- RNG: generators, init kernel per hash, bench kernel ----------------
     for rng in RNGS:
-        w("namespace ref_rng_%s {\n" % rng)
+        w("namespace ns_rng_%s {\n" % rng)
         w(cl(ref, "cl_ops/rng/clo_rng_workitem.cl"))
         w(cl(ref, "cl_ops/rng/clo_rng_%s.cl" % rng))
         w(cl(ref, "cl_ops/rng/clo_rng_api.cl"))
@@ -98,27 +98,27 @@ def generate(ref):
         for hname in HASHES:
             # clo_rng.c:125-127: clo_rng_init over seeds_count work-items
             w('extern "C" void ref_rng_init_%s_%s(unsigned long main_seed, void* seeds, size_t count) {\n'
-              "\tclo_ref_run_serial(count, 1, [&]() { ref_rng_%s::init_%s::clo_rng_init(main_seed, "
-              "(ref_rng_%s::clo_statetype*) seeds); });\n}\n" % (rng, hname, rng, hname, rng))
+              "\tclo_ref_run_serial(count, 1, [&]() { ns_rng_%s::init_%s::clo_rng_init(main_seed, "
+              "(ns_rng_%s::clo_statetype*) seeds); });\n}\n" % (rng, hname, rng, hname, rng))
         # clo_rng_bench.c:302-324: `runs` launches of clo_rng_bench, row r of the output each
         w('extern "C" void ref_rng_bench_%s(void* seeds, unsigned* result, size_t G, size_t runs, '
           "unsigned bits, unsigned maxint) {\n"
           "\tfor (size_t r = 0; r < runs; ++r) {\n"
-          "\t\tif (maxint) clo_ref_run_serial(G, 1, [&]() { ref_rng_%s::bench_maxint::clo_rng_bench("
-          "(ref_rng_%s::clo_statetype*) seeds, result + r * G, maxint); });\n"
-          "\t\telse clo_ref_run_serial(G, 1, [&]() { ref_rng_%s::bench_bits::clo_rng_bench("
-          "(ref_rng_%s::clo_statetype*) seeds, result + r * G, bits); });\n"
+          "\t\tif (maxint) clo_ref_run_serial(G, 1, [&]() { ns_rng_%s::bench_maxint::clo_rng_bench("
+          "(ns_rng_%s::clo_statetype*) seeds, result + r * G, maxint); });\n"
+          "\t\telse clo_ref_run_serial(G, 1, [&]() { ns_rng_%s::bench_bits::clo_rng_bench("
+          "(ns_rng_%s::clo_statetype*) seeds, result + r * G, bits); });\n"
           "\t}\n}\n" % (rng, rng, rng, rng, rng))
 
     # ---------------- scan ----------------
     for name, elem, sm in SCAN_VARIANTS:
-        w("namespace ref_scan_%s {\n#define CLO_SCAN_ELEM_TYPE %s\n#define CLO_SCAN_SUM_TYPE %s\n" % (name, elem, sm))
-        w("typedef %s elem_t; typedef %s sum_t;\n" % (elem, sm))
+        w("namespace ns_scan_%s {\n#define CLO_SCAN_ELEM_TYPE %s\n#define CLO_SCAN_SUM_TYPE %s\n" % (name, elem, sm))
+        w("typedef %s selem_t; typedef %s sum_t;\n" % (elem, sm))
         w(cl(ref, "cl_ops/scan/clo_scan_blelloch.cl"))
         w("#undef CLO_SCAN_ELEM_TYPE\n#undef CLO_SCAN_SUM_TYPE\n}\n")
         # host sequence: clo_scan_blelloch.c:130-141 (sizes), :155-195 (three launches)
         w('extern "C" int ref_scan_%s(const void* in, void* out, size_t numel, size_t lws) {\n' % name)
-        w("\tusing namespace ref_scan_%s;\n" % name)
+        w("\tusing namespace ns_scan_%s;\n" % name)
         w("""	if (lws == 0 || numel < 2 * lws) return -1;
 	size_t realws = numel / 2;
 	size_t gws_wgscan = ((realws + lws - 1) / lws) * lws;
@@ -130,7 +130,7 @@ def generate(ref):
 	std::vector<sum_t> aux(2 * lws);
 	std::vector<sum_t> out_pad(gws_addwgsums);
 	clo_ref_run_groups(gws_wgscan, lws, [&]() {
-		workgroupScan((elem_t*) in, out_pad.data(), wgsums.data(), aux.data(), (uint) numel, blocks_per_wg); });
+		workgroupScan((selem_t*) in, out_pad.data(), wgsums.data(), aux.data(), (uint) numel, blocks_per_wg); });
 	if (gws_wgscan > lws) {
 		clo_ref_run_groups(ws_wgsumsscan, ws_wgsumsscan, [&]() { workgroupSumsScan(wgsums.data(), aux.data()); });
 		clo_ref_run_groups(gws_addwgsums, lws, [&]() { addWorkgroupSums(wgsums.data(), out_pad.data(), blocks_per_wg); });
@@ -145,7 +145,7 @@ def generate(ref):
         macros = ("#define CLO_SORT_ELEM_TYPE %s\n#define CLO_SORT_KEY_TYPE %s\n"
                   "#define CLO_SORT_COMPARE(a, b) %s\n#define CLO_SORT_KEY_GET(x) %s\n" % (elem, key, compare, get_key))
         unmac = "#undef CLO_SORT_ELEM_TYPE\n#undef CLO_SORT_KEY_TYPE\n#undef CLO_SORT_COMPARE\n#undef CLO_SORT_KEY_GET\n"
-        w("namespace ref_sort_%s {\n%stypedef %s elem_t; typedef %s key_t;\n" % (name, macros, elem, key))
+        w("namespace ns_sort_%s {\n%stypedef %s selem_t; typedef %s skey_t;\n" % (name, macros, elem, key))
         w("namespace sb {\n" + cl(ref, "cl_ops/sort/clo_sort_sbitonic.cl") + "}\n")
         w("namespace gs {\n" + cl(ref, "cl_ops/sort/clo_sort_gselect.cl") + "}\n")
         if (name, elem, key, compare, get_key) in RADIX_VARIANTS:
@@ -157,40 +157,40 @@ def generate(ref):
         # sbitonic host loop: clo_sort_sbitonic.c:73-118 (gws = nlpo2(n)/2; stages; steps)
         w('extern "C" int ref_sort_sbitonic_%s(void* data, size_t numel) {\n' % name)
         w("""	if (numel < 2 || (numel & (numel - 1))) return -1;
-	using namespace ref_sort_%s;
+	using namespace ns_sort_%s;
 	size_t gws = numel / 2;
 	uint tot_stages = (uint) clo_ref_log2(gws * 2);
 	for (uint stage = 1; stage <= tot_stages; ++stage)
 		for (uint step = stage; step > 0; --step)
-			clo_ref_run_serial(gws, 1, [&]() { sb::sbitonic((elem_t*) data, stage, step); });
+			clo_ref_run_serial(gws, 1, [&]() { sb::sbitonic((selem_t*) data, stage, step); });
 	return 0;
 }
 """ % name)
         # gselect: clo_sort_gselect.c:75-78,110 (gws = numel, one launch)
         w('extern "C" int ref_sort_gselect_%s(const void* in, void* out, size_t numel) {\n' % name)
-        w("\tusing namespace ref_sort_%s;\n"
-          "\tclo_ref_run_serial(numel, 1, [&]() { gs::gselect((elem_t*) in, (elem_t*) out, (ulong) numel); });\n"
+        w("\tusing namespace ns_sort_%s;\n"
+          "\tclo_ref_run_serial(numel, 1, [&]() { gs::gselect((selem_t*) in, (selem_t*) out, (ulong) numel); });\n"
           "\treturn 0;\n}\n" % name)
         if (name, elem, key, compare, get_key) in RADIX_VARIANTS:
             for nb in RADIX_BITS:
                 # satradix host loop: clo_sort_satradix.c:166-169,184-200,242-313; the global scan of the
                 # counters (clo_sort_satradix.c:298-299) is run through the reference scan kernels (uint,uint)
                 w('extern "C" int ref_sort_satradix%d_%s(void* data, size_t numel, size_t lws) {\n' % (nb, name))
-                w("""	using namespace ref_sort_%(name)s;
+                w("""	using namespace ns_sort_%(name)s;
 	const uint radix = 1u << %(nb)d;
 	if (numel < 2 || (numel & (numel - 1))) return -1;
 	if (lws < radix) lws = radix;
 	if (lws > numel || (lws & (lws - 1))) return -1;
 	const size_t numel_eff = numel;
 	const size_t num_wgs = numel_eff / lws + numel_eff %% lws;
-	const uint total_digits = (uint) (sizeof(elem_t) * 8 / %(nb)d);
+	const uint total_digits = (uint) (sizeof(selem_t) * 8 / %(nb)d);
 	const uint array_len = (uint) (numel_eff / num_wgs);
-	std::vector<elem_t> data_aux(numel_eff);
+	std::vector<selem_t> data_aux(numel_eff);
 	std::vector<uint> offsets(num_wgs * radix), counters(num_wgs * radix), counters_sum(num_wgs * radix);
-	std::vector<elem_t> data_local(array_len);
+	std::vector<selem_t> data_local(array_len);
 	std::vector<uint> scan_local(array_len), offsets_local(radix), counters_local(radix);
-	std::vector<key_t> digits_local(array_len);
-	elem_t* d = (elem_t*) data;
+	std::vector<skey_t> digits_local(array_len);
+	selem_t* d = (selem_t*) data;
 	for (uint i = 0; i < total_digits; ++i) {
 		uint start_bit = i * %(nb)d;
 		clo_ref_run_groups(numel_eff, lws, [&]() {

@@ -61,6 +61,28 @@ def main():
         b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out, chk, u
         torch.cuda.empty_cache()
 
+    if "sortcfg" in what:
+        # tuning sweep of the headline kernel: tile configuration x match method
+        n = 1 << args.log2n_sort
+        t_in = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
+        t_out = torch.empty_like(t_in)
+        b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+        for hw in (0, 1):
+            for cfg in (0, 1, 2, 3, 4):
+                os.environ["CLO_RADIX_MATCH_HW"] = str(hw)
+                os.environ["CLO_RADIX_CFG"] = str(cfg)
+                s = clo.CloSort("satradix", ctx, clo.UINT)
+                med, best = timed(lambda: s.with_device_data(q, b_in, b_out, n), args.iters)
+                u = (t_out.to(torch.int64) & 0xFFFFFFFF)
+                ok = bool((u[1:] >= u[:-1]).all().item())
+                del u
+                print(json.dumps({"sortcfg": dict(hw=hw, cfg=cfg, n=n, ms=med, gkeys=n / med / 1e6,
+                                                  frac=36.0 * n / med / 1e6 / peak, sorted=ok)}), flush=True)
+                s.destroy()
+        os.environ.pop("CLO_RADIX_MATCH_HW"); os.environ.pop("CLO_RADIX_CFG")
+        b_in.destroy(); b_out.destroy(); del t_in, t_out
+        torch.cuda.empty_cache()
+
     if "sort64" in what:
         n = 1 << (args.log2n_sort - 1)
         t_in = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda")
