@@ -24,6 +24,7 @@
 #include "device_utils.cuh"
 #include "sort_common.h"
 
+#include <cstring>
 #include <type_traits>
 
 using namespace clo;
@@ -151,12 +152,6 @@ __device__ __forceinline__ u32 match_digit_ballot(u32 d) {
 	return peers;
 }
 
-template <int MATCH_HW>
-__device__ __forceinline__ u32 match_digit(u32 d) {
-	if (MATCH_HW) return __match_any_sync(0xffffffffu, d);
-	return match_digit_ballot(d);
-}
-
 /* A digit functor for the sample-sort partition: bucket = number of splitters
  * (key, global index) that are <= (my key, my global index). */
 struct SplitterArgs {
@@ -166,8 +161,24 @@ struct SplitterArgs {
 	u64 gidx0;              /* global index of element 0 */
 };
 
+/* How a key gets its rank among the equal-digit keys of its warp:
+ *  RANK_BALLOT  digit-match masks from 8 ballots + a leader's read-modify-write of
+ *               the warp's shared histogram.  ~45 ALU-pipe instructions per 32 keys:
+ *               on B200 this alone costs 0.4 ms per 2^28-key pass (tools/ubench_match.cu).
+ *  RANK_ATOMIC  one shared-memory atomicAdd per key on the warp-private histogram.
+ *               The returned value is the stable rank iff the lanes of one warp
+ *               instruction that hit the same address are served in lane order.  B200
+ *               does that (0 violations in 3e8 samples, tools/ubench_match.cu) but it is
+ *               not an architectural guarantee, so the kernel does not trust it: each
+ *               staged tile is VERIFIED -- (digit << 16 | index-in-tile) must be strictly
+ *               increasing along the staged order, which holds iff the tile-local
+ *               partition is stable -- and a tile that fails is re-ranked with
+ *               RANK_BALLOT and rewritten before the kernel moves on.  Correctness never
+ *               depends on the atomic order; only speed does. */
+enum { RANK_BALLOT = 0, RANK_ATOMIC = 1 };
+
 template <typename ElemT, bool HAS_VAL, bool IDENTITY, bool PARTITION, typename LbT,
-	int THREADS, int IPT, int MATCH_HW>
+	int THREADS, int IPT, int RANK_MODE>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 384 ? 2 : 4))
 clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
@@ -175,15 +186,18 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		u32 start_bit, u32 dmask, CloKeySpec ks, SplitterArgs sp, int* __restrict__ err_flag) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int TILE = THREADS * IPT;
+	constexpr bool VERIFY = (RANK_MODE == RANK_ATOMIC);
 	static_assert(THREADS >= RADIX, "one thread per digit is needed");
+	static_assert(TILE <= 65536, "index-in-tile must fit 16 bits");
 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	u32* whist = reinterpret_cast<u32*>(smem_raw);                         /* [WARPS][RADIX] */
 	u32* s_dstart = whist + WARPS * RADIX;                                 /* [RADIX] */
 	LbT* s_goff = reinterpret_cast<LbT*>(s_dstart + RADIX);                /* [RADIX] (u64-sized slot) */
-	u32* s_misc = s_dstart + RADIX + 2 * RADIX;                            /* [16]: tile, warp sums */
+	u32* s_misc = s_dstart + RADIX + 2 * RADIX;                            /* [16]: tile, warp sums, flags */
 	ElemT* skeys = reinterpret_cast<ElemT*>(s_misc + 16);                  /* [TILE] */
-	u32* svals = reinterpret_cast<u32*>(skeys + TILE);                     /* [TILE] if HAS_VAL */
+	u32* sinfo = reinterpret_cast<u32*>(skeys + TILE);                     /* [TILE] digit<<16 | index */
+	u32* svals = sinfo + TILE;                                             /* [TILE] if HAS_VAL */
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -237,47 +251,55 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		return radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
 	};
 
-	/* ---- rank inside the warp */
 	u32* wh = whist + warp * RADIX;
-#pragma unroll
-	for (int i = 0; i < IPT; ++i) {
-		const u32 local = wbase + i * 32u;
-		const bool valid = full || local < tile_count;
-		const u32 d = digit_of(key[i], local);
-		u32 peers = match_digit<MATCH_HW>(d);
-		if (!full) peers &= __ballot_sync(0xffffffffu, valid);
-		const u32 lt = peers & lanemask_lt();
-		u32 old = 0;
-		if (valid && lt == 0) {            /* first lane of its digit group */
-			old = wh[d];
-			wh[d] = old + __popc(peers);
-		}
-		__syncwarp();
-		const int leader = __ffs(peers) - 1;
-		old = __shfl_sync(0xffffffffu, old, leader & 31);
-		pos[i] = old + __popc(lt);
-	}
-	__syncthreads();
 
-	/* ---- per digit (thread d): warp offsets, tile count, look-back */
-	u32 count = 0;
-	if (tid < RADIX) {
+	/* ---- rank inside the warp: pos[i] = number of earlier keys of this warp with my digit;
+	 *      afterwards wh[d] = number of keys of this warp with digit d */
+	auto rank_ballot = [&]() {
 #pragma unroll
-		for (int w = 0; w < WARPS; ++w) {
-			const u32 c = whist[w * RADIX + tid];
-			whist[w * RADIX + tid] = count;
-			count += c;
+		for (int i = 0; i < IPT; ++i) {
+			const u32 local = wbase + i * 32u;
+			const bool valid = full || local < tile_count;
+			const u32 d = digit_of(key[i], local);
+			u32 peers = match_digit_ballot(d);
+			if (!full) peers &= __ballot_sync(0xffffffffu, valid);
+			const u32 lt = peers & lanemask_lt();
+			u32 old = 0;
+			if (valid && lt == 0) {            /* first lane of its digit group */
+				old = wh[d];
+				wh[d] = old + __popc(peers);
+			}
+			__syncwarp();
+			const int leader = __ffs(peers) - 1;
+			old = __shfl_sync(0xffffffffu, old, leader & 31);
+			pos[i] = old + __popc(lt);
 		}
-	}
-	/* publish the tile aggregate as early as possible */
-	LbT* lb_mine = lookback + (size_t) tile * RADIX;
-	if (tid < RADIX) {
-		if (tile == 0) st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | (LbT) count));
-		else st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::AGG | (LbT) count));
-	}
-	/* exclusive scan of the 256 counts -> start of each digit inside the tile */
-	{
-		u32 incl = warp_inclusive_scan<u32>(count, lane);
+	};
+	auto rank_atomic = [&]() {
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			const u32 local = wbase + i * 32u;
+			if (full || local < tile_count) pos[i] = atomicAdd(&wh[digit_of(key[i], local)], 1u);
+		}
+	};
+
+	/* ---- per digit (thread d): exclusive offsets of the warps, tile count */
+	auto digit_count = [&]() -> u32 {
+		u32 count = 0;
+		if (tid < RADIX) {
+#pragma unroll
+			for (int w = 0; w < WARPS; ++w) {
+				const u32 c = whist[w * RADIX + tid];
+				whist[w * RADIX + tid] = count;
+				count += c;
+			}
+		}
+		return count;
+	};
+	/* exclusive scan of the 256 counts -> start of each digit inside the tile, folded into
+	 * the per-warp offsets so that staging needs one table lookup (contains a barrier) */
+	auto digit_starts = [&](u32 count) {
+		const u32 incl = warp_inclusive_scan<u32>(count, lane);
 		if (tid < RADIX && lane == 31) s_misc[1 + warp] = incl;
 		__syncthreads();
 		if (tid < RADIX) {
@@ -286,11 +308,55 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[1 + w];
 			const u32 ds = off + incl - count;
 			s_dstart[tid] = ds;
-			/* fold the digit start into the per-warp offsets: one table lookup when staging */
 #pragma unroll
 			for (int w = 0; w < WARPS; ++w) whist[w * RADIX + tid] += ds;
 		}
+	};
+	/* ---- stage the tile in digit order */
+	auto stage = [&]() {
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			const u32 local = wbase + i * 32u;
+			if (full || local < tile_count) {
+				const u32 d = digit_of(key[i], local);
+				const u32 p = wh[d] + pos[i];
+				skeys[p] = key[i];
+				sinfo[p] = (d << 16) | local;
+				if (HAS_VAL) svals[p] = val[i];
+			}
+		}
+	};
+	/* ---- write out: element j of the staged tile -> goff[digit] + j.  Returns whether
+	 *      the staged order was seen to be unstable (VERIFY only). */
+	auto write_out = [&](bool verify) -> bool {
+		bool bad = false;
+#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			const u32 j = (u32) tid + i * THREADS;
+			if (full || j < tile_count) {
+				const u32 info = sinfo[j];
+				if (verify && j > 0 && info <= sinfo[j - 1]) bad = true;
+				const LbT o = s_goff[info >> 16] + (LbT) j;
+				out[o] = skeys[j];
+				if (HAS_VAL) vout[o] = svals[j];
+			}
+		}
+		return bad;
+	};
+
+	if (RANK_MODE == RANK_ATOMIC) rank_atomic(); else rank_ballot();
+	__syncthreads();
+
+	const u32 count = digit_count();
+	/* publish the tile aggregate as early as possible */
+	LbT* lb_mine = lookback + (size_t) tile * RADIX;
+	if (tid < RADIX) {
+		if (tile == 0) st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | (LbT) count));
+		else st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::AGG | (LbT) count));
 	}
+	digit_starts(count);
+
+	/* ---- decoupled look-back, one digit per thread */
 	if (tid < RADIX) {
 		LbT excl = 0;
 		if (tile > 0) {
@@ -324,47 +390,25 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	}
 	__syncthreads();
 
-	/* ---- stage the tile in digit order */
-#pragma unroll
-	for (int i = 0; i < IPT; ++i) {
-		const u32 local = wbase + i * 32u;
-		if (full || local < tile_count) {
-			const u32 d = digit_of(key[i], local);
-			const u32 p = wh[d] + pos[i];
-			skeys[p] = key[i];
-			if (HAS_VAL) svals[p] = val[i];
-			if (PARTITION) pos[i] = p;
-		}
-	}
+	stage();
 	__syncthreads();
+	const bool bad = write_out(VERIFY);
 
-	/* ---- write out: thread j of the staged tile -> goff[digit] + j */
-	if (!PARTITION) {
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 j = (u32) tid + i * THREADS;
-			if (full || j < tile_count) {
-				const ElemT k = skeys[j];
-				const u32 d = radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
-				const LbT o = s_goff[d] + (LbT) j;
-				out[o] = k;
-				if (HAS_VAL) vout[o] = svals[j];
-			}
-		}
-	} else {
-		/* the bucket of a staged element is not recomputable from the key alone
-		 * (ties are broken by global index): find it from the digit starts */
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 j = (u32) tid + i * THREADS;
-			if (full || j < tile_count) {
-				u32 d = 0;
-#pragma unroll
-				for (int s = 1; s < 16; ++s) if (s <= (int) sp.count && j >= s_dstart[s]) d = s;
-				const LbT o = s_goff[d] + (LbT) j;
-				out[o] = skeys[j];
-				if (HAS_VAL) vout[o] = svals[j];
-			}
+	if (VERIFY) {
+		if (__syncthreads_or(bad ? 1 : 0)) {
+			/* The atomic ranks were not in lane order somewhere in this tile: redo the tile
+			 * with the ballot ranks.  Digit counts, hence every offset, are unchanged. */
+			if (tid == 0) atomicAdd(err_flag + 1, 1);
+			for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+			__syncthreads();
+			rank_ballot();
+			__syncthreads();
+			const u32 count2 = digit_count();
+			digit_starts(count2);
+			__syncthreads();
+			stage();
+			__syncthreads();
+			write_out(false);
 		}
 	}
 }
@@ -380,7 +424,8 @@ template <typename ElemT, bool HAS_VAL> struct TileCfg {
 template <typename ElemT, bool HAS_VAL, int THREADS, int IPT>
 constexpr size_t onesweep_smem() {
 	return (size_t) (THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8 + 16 * 4 +
-		(size_t) THREADS * IPT * sizeof(ElemT) + (HAS_VAL ? (size_t) THREADS * IPT * 4 : 0);
+		(size_t) THREADS * IPT * sizeof(ElemT) + (size_t) THREADS * IPT * 4 +
+		(HAS_VAL ? (size_t) THREADS * IPT * 4 : 0);
 }
 
 } // namespace
@@ -389,14 +434,14 @@ struct CloRadixState {
 	CloScratch aux_keys;     /* ping-pong partner of the key buffer */
 	CloScratch aux_vals;
 	CloScratch work;         /* [err | ghist | bins_base | tickets | lookback...] */
-	int match_hw = 0;
+	int rank_atomic = 1;     /* CLO_RADIX_RANK=ballot selects the ballot ranks */
 	int cfg = 0;
 };
 
 CloRadixState* clo_radix_state_new() {
 	CloRadixState* st = new CloRadixState();
-	const char* e = getenv("CLO_RADIX_MATCH_HW");
-	st->match_hw = (e && *e == '1') ? 1 : 0;
+	const char* e = getenv("CLO_RADIX_RANK");
+	st->rank_atomic = (e && strcmp(e, "ballot") == 0) ? 0 : 1;
 	const char* c = getenv("CLO_RADIX_CFG");
 	st->cfg = (c && *c) ? atoi(c) : 0;
 	return st;
@@ -442,12 +487,12 @@ cudaError_t prepare_work(CloRadixState* st, size_t tiles, int passes, size_t lb_
 	return cudaMemsetAsync(base, 0, L.zero_bytes, stream);
 }
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int MATCH_HW, int THREADS, int IPT>
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int RANK_MODE, int THREADS, int IPT>
 cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n,
 		LbT* lookback, u32* ticket, const u64* bins, u32 start_bit, u32 dmask, const CloKeySpec& ks,
 		int* err, cudaStream_t stream) {
 	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT>();
-	auto kern = clo_radix_onesweep<ElemT, HAS_VAL, IDENTITY, false, LbT, THREADS, IPT, MATCH_HW>;
+	auto kern = clo_radix_onesweep<ElemT, HAS_VAL, IDENTITY, false, LbT, THREADS, IPT, RANK_MODE>;
 	static bool configured[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -517,12 +562,12 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		u32* ticket = L.tickets + p;
 		if (wide) {
 			u64* lb = (u64*) L.lookback + (size_t) p * tiles * RADIX;
-			e = st->match_hw
+			e = st->rank_atomic
 				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
 				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		} else {
 			u32* lb = (u32*) L.lookback + (size_t) p * tiles * RADIX;
-			e = st->match_hw
+			e = st->rank_atomic
 				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
 				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		}
@@ -547,7 +592,7 @@ cudaError_t radix_sort_typed<u32, false, true>(CloRadixState* st, int sm_count, 
 	switch (st->cfg) {
 	case 1: return radix_sort_cfg<u32, false, true, 256, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	case 2: return radix_sort_cfg<u32, false, true, 384, 18>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 3: return radix_sort_cfg<u32, false, true, 256, 24>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 3: return radix_sort_cfg<u32, false, true, 256, 12>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	case 4: return radix_sort_cfg<u32, false, true, 512, 12>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	default: return radix_sort_cfg<u32, false, true, 512, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	}
@@ -661,11 +706,11 @@ cudaError_t partition_typed(CloRadixState* st, const ElemT* in, const u32* vin, 
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if (n == 0) return cudaSuccess;
 	if (wide) {
-		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u64, THREADS, IPT, 0>;
+		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u64, THREADS, IPT, RANK_BALLOT>;
 		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
 		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u64*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err);
 	} else {
-		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u32, THREADS, IPT, 0>;
+		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u32, THREADS, IPT, RANK_BALLOT>;
 		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
 		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u32*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err);
 	}

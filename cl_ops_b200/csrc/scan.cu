@@ -12,6 +12,7 @@
 #include "clo_internal.h"
 #include "device_utils.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -58,13 +59,16 @@ const unsigned SPIN_LIMIT = 1u << 26;
 
 /* ------------------------------------------------------------------ kernel */
 
-/* Persistent, software-pipelined single-pass scan.  A CTA repeatedly takes a tile
- * ticket; the loads of its NEXT tile are issued before it waits on the look-back
- * of the current one, so HBM stays busy while prefixes propagate. */
-template <typename ElemT, typename SumT, int THREADS, int VPT>
-__global__ void __launch_bounds__(THREADS)
-clo_scan_lookback(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 num_tiles,
-		u64* __restrict__ desc, u32* __restrict__ ticket, u32 ticket_base, u32 epoch,
+/* One tile per CTA; tile index = blockIdx.x.  The look-back assumes that a CTA with a
+ * lower index is never scheduled after one with a higher index (the order the hardware
+ * work distributor uses for a 1-D grid, and the assumption behind cub::DeviceScan as
+ * well); the spin bound turns a violation into an error flag instead of a hang.  Many
+ * small CTAs per SM let the scheduler overlap one tile's look-back wait with the loads
+ * of the others. */
+template <typename ElemT, typename SumT, int THREADS, int VPT, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
+clo_scan_lookback(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n,
+		u64* __restrict__ desc, u32 epoch,
 		const SumT* __restrict__ carry_in, int vec_in, int vec_out, int* __restrict__ err_flag) {
 	typedef typename AccOf<SumT>::type AccT;
 	typedef AccWords<AccT> AW;
@@ -74,165 +78,145 @@ clo_scan_lookback(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n
 	/* output chunk: at most 16 bytes per store */
 	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
 
-	__shared__ u32 s_next;
 	__shared__ AccT s_warp[WARPS];
 	__shared__ AccT s_prefix;
 
+	const u32 tile = blockIdx.x;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const u32 lane_off = ((u32) (warp * VPT) * 32u + lane) * EPV;   /* + j*32*EPV per row */
+	const size_t tile_base = (size_t) tile * TILE;
+	const bool full = tile_base + TILE <= n;
 
-	auto load_tile = [&](u32 t, ElemT (&e)[VPT][EPV]) {
-		const size_t tile_base = (size_t) t * TILE;
-		const bool full = tile_base + TILE <= n;
+	/* ---- load: warp-striped vectors (row j of warp w is 32*EPV contiguous elements) */
+	AccT v[VPT][EPV];
 #pragma unroll
-		for (int j = 0; j < VPT; ++j) {
-			const size_t idx = tile_base + lane_off + (size_t) j * 32 * EPV;
-			if (vec_in && (full || idx + EPV <= n)) {
-				load_vec_cs<ElemT, EPV>(in + idx, e[j]);
-			} else {
+	for (int j = 0; j < VPT; ++j) {
+		const size_t idx = tile_base + ((size_t) (warp * VPT + j) * 32 + lane) * EPV;
+		ElemT e[EPV];
+		if (vec_in && (full || idx + EPV <= n)) {
+			load_vec_cs<ElemT, EPV>(in + idx, e);
+		} else {
 #pragma unroll
-				for (int c = 0; c < EPV; ++c) e[j][c] = (idx + c < n) ? in[idx + c] : ElemT(0);
-			}
+			for (int c = 0; c < EPV; ++c) e[c] = (idx + c < n) ? in[idx + c] : ElemT(0);
 		}
-	};
+#pragma unroll
+		for (int c = 0; c < EPV; ++c) v[j][c] = to_acc<ElemT, SumT, AccT>(e[c]);
+	}
 
-	if (threadIdx.x == 0) s_next = atomicAdd(ticket, 1u) - ticket_base;
+	/* ---- thread: inclusive scan inside each vector; warp: scan of vector sums per row */
+	AccT base[VPT];
+	AccT warp_total = AccT(0);
+#pragma unroll
+	for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+		for (int c = 1; c < EPV; ++c) v[j][c] += v[j][c - 1];
+		AccT incl = warp_inclusive_scan<AccT>(v[j][EPV - 1], lane);
+		AccT excl = __shfl_up_sync(0xffffffffu, incl, 1);
+		if (lane == 0) excl = AccT(0);
+		AccT row_total = __shfl_sync(0xffffffffu, incl, 31);
+		base[j] = warp_total + excl;
+		warp_total += row_total;
+	}
+
+	/* ---- block: offsets of the warps, tile aggregate */
+	if (lane == 0) s_warp[warp] = warp_total;
 	__syncthreads();
-	u32 tile = s_next;
-	__syncthreads();
-	if (tile >= num_tiles) return;
-	const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
-	const u64 fl_agg = ((u64) ((epoch << 2) | ST_AGG)) << 32;
-	const u64 fl_pre = ((u64) ((epoch << 2) | ST_PREFIX)) << 32;
-
-	ElemT cur[VPT][EPV];
-	load_tile(tile, cur);
-
-	for (;;) {
-		/* ticket of the next tile: issued now, consumed after the local scan */
-		u32 tk = 0;
-		if (threadIdx.x == 0) tk = atomicAdd(ticket, 1u) - ticket_base;
-
-		/* ---- thread: inclusive scan inside each vector; warp: scan of vector sums per row */
-		AccT v[VPT][EPV];
-		AccT base[VPT];
-		AccT warp_total = AccT(0);
+	AccT warp_off = AccT(0), aggregate = AccT(0);
 #pragma unroll
-		for (int j = 0; j < VPT; ++j) {
-#pragma unroll
-			for (int c = 0; c < EPV; ++c) v[j][c] = to_acc<ElemT, SumT, AccT>(cur[j][c]);
-#pragma unroll
-			for (int c = 1; c < EPV; ++c) v[j][c] += v[j][c - 1];
-			AccT incl = warp_inclusive_scan<AccT>(v[j][EPV - 1], lane);
-			AccT excl = __shfl_up_sync(0xffffffffu, incl, 1);
-			if (lane == 0) excl = AccT(0);
-			AccT row_total = __shfl_sync(0xffffffffu, incl, 31);
-			base[j] = warp_total + excl;
-			warp_total += row_total;
-		}
+	for (int w = 0; w < WARPS; ++w) {
+		AccT t = s_warp[w];
+		if (w < warp) warp_off += t;
+		aggregate += t;
+	}
 
-		/* ---- block: offsets of the warps, tile aggregate */
-		if (lane == 0) s_warp[warp] = warp_total;
-		if (threadIdx.x == 0) s_next = tk;
-		__syncthreads();
-		AccT warp_off = AccT(0), aggregate = AccT(0);
-#pragma unroll
-		for (int w = 0; w < WARPS; ++w) {
-			AccT t = s_warp[w];
-			if (w < warp) warp_off += t;
-			aggregate += t;
-		}
-		const u32 next_tile = s_next;
+	/* ---- decoupled look-back (warp 0; lane i inspects tile-1-i) */
+	if (warp == 0) {
+		const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
+		const u64 fl_agg = ((u64) ((epoch << 2) | ST_AGG)) << 32;
+		const u64 fl_pre = ((u64) ((epoch << 2) | ST_PREFIX)) << 32;
 		u64* mine = desc + (size_t) tile * AW::N;
-		if (threadIdx.x == 0) {
-			/* publish as early as possible: tile 0 knows its inclusive prefix already */
-			u32 w[AW::N];
-			AW::pack(tile == 0 ? (AccT) (carry + aggregate) : aggregate, w);
+		AccT exclusive = carry;
+		if (tile == 0) {
+			if (lane == 0) {
+				u32 w[AW::N];
+				AW::pack(carry + aggregate, w);
 #pragma unroll
-			for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, (tile == 0 ? fl_pre : fl_agg) | w[k]);
-		}
-
-		/* ---- prefetch the next tile before waiting on predecessors */
-		const bool more = next_tile < num_tiles;
-		if (more) load_tile(next_tile, cur);
-
-		/* ---- decoupled look-back (warp 0; lane i inspects tile-1-i) */
-		if (warp == 0) {
-			AccT exclusive = carry;
-			if (tile != 0) {
-				exclusive = AccT(0);
-				long long look = (long long) tile - 1;
-				unsigned spins = 0;
-				bool done = false;
-				while (!done) {
-					const long long idx = look - lane;
-					u32 state = ST_PREFIX;  /* lanes before tile 0 act as an empty prefix */
-					AccT val = AccT(0);
-					if (idx >= 0) {
-						const u64* p = desc + (size_t) idx * AW::N;
-						for (;;) {
-							u32 w[AW::N];
-							u32 st = 0;
-							bool ok = true;
+				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
+			}
+		} else {
+			if (lane == 0) {
+				u32 w[AW::N];
+				AW::pack(aggregate, w);
 #pragma unroll
-							for (int k = 0; k < AW::N; ++k) {
-								const u64 x = ld_relaxed(p + k);
-								const u32 f = (u32) (x >> 32);
-								w[k] = (u32) x;
-								if ((f >> 2) != epoch || (f & 3u) == 0) ok = false;
-								if (k == 0) st = f & 3u; else if ((f & 3u) != st) ok = false;
-							}
-							if (ok) { state = st; val = AW::unpack(w); break; }
-							if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
+				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_agg | w[k]);
+			}
+			exclusive = AccT(0);
+			long long look = (long long) tile - 1;
+			unsigned spins = 0;
+			bool done = false;
+			while (!done) {
+				const long long idx = look - lane;
+				u32 state = ST_PREFIX;  /* lanes before tile 0 act as an empty prefix */
+				AccT val = AccT(0);
+				if (idx >= 0) {
+					const u64* p = desc + (size_t) idx * AW::N;
+					for (;;) {
+						u32 w[AW::N];
+						u32 st = 0;
+						bool ok = true;
+#pragma unroll
+						for (int k = 0; k < AW::N; ++k) {
+							const u64 x = ld_relaxed(p + k);
+							const u32 f = (u32) (x >> 32);
+							w[k] = (u32) x;
+							if ((f >> 2) != epoch || (f & 3u) == 0) ok = false;
+							if (k == 0) st = f & 3u; else if ((f & 3u) != st) ok = false;
 						}
+						if (ok) { state = st; val = AW::unpack(w); break; }
+						if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
 					}
-					const u32 pmask = __ballot_sync(0xffffffffu, state == ST_PREFIX);
-					const int first = pmask ? (__ffs(pmask) - 1) : 32;
-					AccT contrib = (lane <= first) ? val : AccT(0);
-					exclusive += warp_reduce_sum<AccT>(contrib);
-					done = (pmask != 0);
-					look -= 32;
+				} else if (idx == -1) {
+					val = carry;   /* the scan's carry-in sits "before tile 0" */
 				}
-				if (lane == 0) {
-					u32 w[AW::N];
-					AW::pack(exclusive + aggregate, w);
-#pragma unroll
-					for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
-				}
+				const u32 pmask = __ballot_sync(0xffffffffu, state == ST_PREFIX);
+				const int first = pmask ? (__ffs(pmask) - 1) : 32;
+				AccT contrib = (lane <= first) ? val : AccT(0);
+				exclusive += warp_reduce_sum<AccT>(contrib);
+				done = (pmask != 0);
+				look -= 32;
 			}
-			if (lane == 0) s_prefix = exclusive;
+			if (lane == 0) {
+				u32 w[AW::N];
+				AW::pack(exclusive + aggregate, w);
+#pragma unroll
+				for (int k = 0; k < AW::N; ++k) st_relaxed(mine + k, fl_pre | w[k]);
+			}
 		}
-		__syncthreads();
-		const AccT tile_prefix = s_prefix + warp_off;
+		if (lane == 0) s_prefix = exclusive;
+	}
+	__syncthreads();
+	const AccT tile_prefix = s_prefix + warp_off;
 
-		/* ---- store: same warp-striped layout */
-		{
-			const size_t tile_base = (size_t) tile * TILE;
-			const bool full = tile_base + TILE <= n;
+	/* ---- store: same warp-striped layout */
 #pragma unroll
-			for (int j = 0; j < VPT; ++j) {
-				const size_t idx = tile_base + lane_off + (size_t) j * 32 * EPV;
-				const AccT b = tile_prefix + base[j];
-				SumT o[EPV];
-				o[0] = static_cast<SumT>(b);
+	for (int j = 0; j < VPT; ++j) {
+		const size_t idx = tile_base + ((size_t) (warp * VPT + j) * 32 + lane) * EPV;
+		const AccT b = tile_prefix + base[j];
+		SumT o[EPV];
+		o[0] = static_cast<SumT>(b);
 #pragma unroll
-				for (int c = 1; c < EPV; ++c) o[c] = static_cast<SumT>(b + v[j][c - 1]);
-				if (vec_out && (full || idx + EPV <= n)) {
+		for (int c = 1; c < EPV; ++c) o[c] = static_cast<SumT>(b + v[j][c - 1]);
+		if (vec_out && (full || idx + EPV <= n)) {
 #pragma unroll
-					for (int c0 = 0; c0 < EPV; c0 += OCH) {
-						SumT chunk[OCH];
+			for (int c0 = 0; c0 < EPV; c0 += OCH) {
+				SumT chunk[OCH];
 #pragma unroll
-						for (int c = 0; c < OCH; ++c) chunk[c] = o[c0 + c];
-						store_vec_cs<SumT, OCH>(out + idx + c0, chunk);
-					}
-				} else {
-#pragma unroll
-					for (int c = 0; c < EPV; ++c) if (idx + c < n) out[idx + c] = o[c];
-				}
+				for (int c = 0; c < OCH; ++c) chunk[c] = o[c0 + c];
+				store_vec_cs<SumT, OCH>(out + idx + c0, chunk);
 			}
+		} else {
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) if (idx + c < n) out[idx + c] = o[c];
 		}
-		if (!more) break;
-		tile = next_tile;
 	}
 }
 
@@ -282,63 +266,71 @@ __global__ void clo_scan_reduce_final(const typename AccOf<SumT>::type* __restri
 
 /* --------------------------------------------------------------- host side */
 
-const int SCAN_THREADS = 256;
-const int SCAN_VPT = 4;
-
 struct ScanState {
-	CloScratch scratch;        /* [ticket(u32) | err(int) | pad | descriptors...] */
+	CloScratch scratch;        /* [pad | err(int) | pad | descriptors...] */
 	size_t tiles_cap = 0;
 	u32 epoch = 0;
-	u32 ticket_base = 0;
+	int cfg = 0;               /* CLO_SCAN_CFG: tile shape variants of the u32->u32 kernel */
 	CloScratch partials;
 };
 
 const size_t HDR_BYTES = 256;
 
-template <typename ElemT, typename SumT>
-cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) {
-	typedef typename AccOf<SumT>::type AccT;
+/* default tile: 128 threads x 4 vectors (2048 4-byte elements), >= 10 CTAs per SM */
+const int SCAN_THREADS = 128;
+const int SCAN_VPT = 4;
+const int SCAN_MIN_CTAS = 10;
+
+template <typename ElemT, typename SumT, int THREADS, int VPT, int MIN_CTAS>
+cudaError_t launch_scan_cfg(ScanState& st, const void* in, void* out, size_t n, const void* carry, cudaStream_t stream) {
 	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
-	constexpr size_t TILE = (size_t) SCAN_THREADS * SCAN_VPT * EPV;
+	constexpr size_t TILE = (size_t) THREADS * VPT * EPV;
 	const size_t tiles = (n + TILE - 1) / TILE;
-	if (tiles >= 0xffffffffull) return cudaErrorInvalidValue;
+	if (tiles >= 0x7fffffffull) return cudaErrorInvalidValue;
 	cudaError_t e;
 	if (tiles > st.tiles_cap) {
 		/* descriptors are sized for the widest accumulator (2 words) */
 		size_t cap = tiles + tiles / 4 + 1024;
 		if ((e = st.scratch.reserve(HDR_BYTES + cap * 2 * sizeof(u64))) != cudaSuccess) return e;
 		if ((e = cudaMemsetAsync(st.scratch.ptr, 0, st.scratch.size, stream)) != cudaSuccess) return e;
-		st.tiles_cap = cap; st.epoch = 0; st.ticket_base = 0;
+		st.tiles_cap = cap; st.epoch = 0;
 	}
 	if (st.epoch >= (1u << 30) - 2) {
 		if ((e = cudaMemsetAsync(st.scratch.ptr, 0, st.scratch.size, stream)) != cudaSuccess) return e;
-		st.epoch = 0; st.ticket_base = 0;
+		st.epoch = 0;
 	}
+	/* descriptors of earlier calls carry an older epoch and read as "not published" */
 	st.epoch += 1;
-	u32* ticket = (u32*) st.scratch.ptr;
 	int* err_flag = (int*) st.scratch.ptr + 1;
 	u64* desc = (u64*) ((char*) st.scratch.ptr + HDR_BYTES);
 	const int vec_in = (reinterpret_cast<uintptr_t>(in) % (sizeof(ElemT) * EPV)) == 0;
 	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
 	const int vec_out = (reinterpret_cast<uintptr_t>(out) % (sizeof(SumT) * OCH)) == 0;
-	/* persistent grid: as many CTAs as fit on the device at once (never more than tiles) */
-	static int ctas_per_sm = 0;
-	if (!ctas_per_sm) {
-		int k = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, clo_scan_lookback<ElemT, SumT, SCAN_THREADS, SCAN_VPT>,
-				SCAN_THREADS, 0) != cudaSuccess || k < 1) k = 2;
-		ctas_per_sm = k;
-	}
-	size_t grid = (size_t) sms * ctas_per_sm;
-	if (grid > tiles) grid = tiles;
-	clo_scan_lookback<ElemT, SumT, SCAN_THREADS, SCAN_VPT><<<(unsigned) grid, SCAN_THREADS, 0, stream>>>(
-		(const ElemT*) in, (SumT*) out, n, (u32) tiles, desc, ticket, st.ticket_base, st.epoch,
-		(const SumT*) carry, vec_in, vec_out, err_flag);
+	clo_scan_lookback<ElemT, SumT, THREADS, VPT, MIN_CTAS><<<(unsigned) tiles, THREADS, 0, stream>>>(
+		(const ElemT*) in, (SumT*) out, n, desc, st.epoch, (const SumT*) carry, vec_in, vec_out, err_flag);
 	CLO_COUNT_LAUNCH(1);
-	/* every CTA draws one ticket past the end before it exits */
-	st.ticket_base += (u32) (tiles + grid);
-	(void) sizeof(AccT);
 	return cudaGetLastError();
+}
+
+template <typename ElemT, typename SumT>
+cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) {
+	(void) sms;
+	return launch_scan_cfg<ElemT, SumT, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream);
+}
+
+/* tuning variants of the headline type pair */
+template <>
+cudaError_t launch_scan<unsigned int, unsigned int>(ScanState& st, const void* in, void* out, size_t n,
+		const void* carry, int sms, cudaStream_t stream) {
+	(void) sms;
+	switch (st.cfg) {
+	case 1: return launch_scan_cfg<unsigned int, unsigned int, 256, 4, 5>(st, in, out, n, carry, stream);
+	case 2: return launch_scan_cfg<unsigned int, unsigned int, 128, 8, 6>(st, in, out, n, carry, stream);
+	case 3: return launch_scan_cfg<unsigned int, unsigned int, 64, 4, 16>(st, in, out, n, carry, stream);
+	case 4: return launch_scan_cfg<unsigned int, unsigned int, 256, 8, 3>(st, in, out, n, carry, stream);
+	case 5: return launch_scan_cfg<unsigned int, unsigned int, 128, 4, 16>(st, in, out, n, carry, stream);
+	default: return launch_scan_cfg<unsigned int, unsigned int, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream);
+	}
 }
 
 template <typename ElemT, typename SumT>
@@ -533,6 +525,7 @@ extern "C" CloScan* clo_scan_new(const char* type, const char* options, CCLConte
 	s->elem_type = elem_type; s->sum_type = sum_type;
 	s->data = NULL;
 	s->fn = fn; s->rfn = find_reduce((int) elem_type, (int) sum_type);
+	{ const char* c = getenv("CLO_SCAN_CFG"); s->st.cfg = (c && *c) ? atoi(c) : 0; }
 	GError* ierr = NULL;
 	s->impl_def.init(s, options, &ierr);
 	if (ierr) { g_propagate_error(err, ierr); clo_scan_destroy(s); return NULL; }

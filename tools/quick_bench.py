@@ -67,9 +67,9 @@ def main():
         t_in = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
         t_out = torch.empty_like(t_in)
         b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
-        for hw in (0, 1):
+        for hw in ("atomic", "ballot"):
             for cfg in (0, 1, 2, 3, 4):
-                os.environ["CLO_RADIX_MATCH_HW"] = str(hw)
+                os.environ["CLO_RADIX_RANK"] = hw
                 os.environ["CLO_RADIX_CFG"] = str(cfg)
                 s = clo.CloSort("satradix", ctx, clo.UINT)
                 med, best = timed(lambda: s.with_device_data(q, b_in, b_out, n), args.iters)
@@ -79,7 +79,7 @@ def main():
                 print(json.dumps({"sortcfg": dict(hw=hw, cfg=cfg, n=n, ms=med, gkeys=n / med / 1e6,
                                                   frac=36.0 * n / med / 1e6 / peak, sorted=ok)}), flush=True)
                 s.destroy()
-        os.environ.pop("CLO_RADIX_MATCH_HW"); os.environ.pop("CLO_RADIX_CFG")
+        os.environ.pop("CLO_RADIX_RANK"); os.environ.pop("CLO_RADIX_CFG")
         b_in.destroy(); b_out.destroy(); del t_in, t_out
         torch.cuda.empty_cache()
 
@@ -149,6 +149,24 @@ def main():
                          frac=bytes_per * n / med / 1e6 / peak, check=ok)
         print(json.dumps({name: res[name]}), flush=True)
         b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out
+        torch.cuda.empty_cache()
+
+    if "scancfg" in what:
+        n = 1 << args.log2n_scan
+        t_in = torch.randint(0, 128, (n,), dtype=torch.int32, device="cuda")
+        t_out = torch.empty_like(t_in)
+        b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+        for cfg in range(6):
+            os.environ["CLO_SCAN_CFG"] = str(cfg)
+            s = clo.CloScan("blelloch", ctx, clo.UINT, clo.UINT)
+            med, best = timed(lambda: s.with_device_data(q, b_in, b_out, n), args.iters)
+            want = int(t_in[:-1].to(torch.int64).sum().item()) & 0xFFFFFFFF
+            got = int(t_out[-1].item()) & 0xFFFFFFFF
+            print(json.dumps({"scancfg": dict(cfg=cfg, n=n, ms=med, gbs=8.0 * n / med / 1e6,
+                                              frac=8.0 * n / med / 1e6 / peak, check=want == got)}), flush=True)
+            s.destroy()
+        os.environ.pop("CLO_SCAN_CFG")
+        b_in.destroy(); b_out.destroy(); del t_in, t_out
         torch.cuda.empty_cache()
 
     if "rng" in what:
