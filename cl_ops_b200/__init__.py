@@ -113,6 +113,9 @@ def lib():
         sig("clo_sort_with_host_data", u32, vp, vp, vp, vp, vp, sz, sz, errp)
         sig("clo_sort_pairs_with_device_data", vp, vp, vp, vp, vp, sz, errp)
         sig("clo_sort_partition_with_device_data", vp, vp, vp, vp, vp, vp, vp, sz, u64, vp, vp, u32, vp, errp)
+        sig("clo_sort_b200_debug", u32, vp, vp, ctypes.POINTER(ctypes.c_uint64))
+        sig("clo_sort_b200_set_timing", None, vp, u32)
+        sig("clo_sort_b200_get_timing", u32, vp, ctypes.POINTER(ctypes.c_float), u32)
         sig("clo_sort_get_element_size", sz, vp)
         sig("clo_sort_get_key_size", sz, vp)
         sig("clo_sort_get_num_kernels", u32, vp, errp)
@@ -295,6 +298,15 @@ class CloSort:
             raise CloError(CLO_ERROR_LIBRARY, "clo_sort_with_host_data failed")
         return out
 
+    def with_host_pointers(self, in_ptr, out_ptr, numel, queue=None, lws_max=0):
+        """clo_sort_with_host_data on raw host addresses (e.g. pinned torch tensors)."""
+        e = _Err()
+        ok = lib().clo_sort_with_host_data(self.h, queue.h if queue else None, None, ctypes.c_void_p(in_ptr),
+                                           ctypes.c_void_p(out_ptr), numel, lws_max, e.ref())
+        e.check()
+        if not ok:
+            raise CloError(CLO_ERROR_LIBRARY, "clo_sort_with_host_data failed")
+
     def with_device_data(self, queue, data_in, data_out, numel, lws_max=0):
         """clo_sort_with_device_data: data_out=None sorts in place. Returns the CCLEvent*."""
         e = _Err()
@@ -319,6 +331,21 @@ class CloSort:
             nparts, counts_out.h, e.ref())
         e.check()
         return evt
+
+    def set_timing(self, on=True):
+        lib().clo_sort_b200_set_timing(self.h, 1 if on else 0)
+
+    def get_timing(self):
+        """[histogram+scan ms, pass0 ms, pass1 ms, ...] of the last radix call."""
+        out = (ctypes.c_float * 12)()
+        k = lib().clo_sort_b200_get_timing(self.h, out, 12)
+        return [float(out[i]) for i in range(k)]
+
+    def debug(self, queue):
+        """[timeout flag, repaired tiles, 16 phase-profile counters] of the last radix call."""
+        out = (ctypes.c_uint64 * 18)()
+        lib().clo_sort_b200_debug(self.h, queue.h, out)
+        return list(out)
 
     def kernel_names(self):
         e = _Err()

@@ -31,11 +31,14 @@ using namespace clo;
 
 namespace {
 
+int g_radix_profile = 0;
+
 const int RADIX_BITS = 8;
 const int RADIX = 1 << RADIX_BITS;
 const int MAX_PASSES = 8;
 const unsigned SPIN_LIMIT = 1u << 26;
-const int LB_BATCH = 4;
+const int LB_FIRST = 4;     /* look-back window: first load batch */
+const int LB_NEXT = 4;      /* ... and the following ones */
 
 struct PassCfg {
 	int passes;
@@ -76,44 +79,64 @@ __device__ __forceinline__ u32 radix_digit(ElemT e, const CloKeySpec& ks, u32 st
 
 /* ------------------------------------------------------------- histogram */
 
-template <typename ElemT, bool IDENTITY, int THREADS>
-__global__ void __launch_bounds__(THREADS)
+/* One read of the keys -> the 256-bin histogram of every digit.
+ * Shared-memory layout [pass][bin][COLS]: lane l only ever touches column l % COLS, so
+ * with COLS == 32 the 32 atomics of a warp instruction hit 32 different banks no matter
+ * what the digits are (uniform or constant keys cost the same: one wavefront).  The
+ * atomics are still needed because the warps of the CTA share the table. */
+template <typename ElemT, bool IDENTITY, int PASSES, int COLS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1)
 clo_radix_histogram(const ElemT* __restrict__ in, size_t n, u64* __restrict__ ghist,
 		PassCfg cfg, CloKeySpec ks, int vec_ok) {
-	__shared__ u32 sh[MAX_PASSES * RADIX];
-	for (int i = threadIdx.x; i < cfg.passes * RADIX; i += THREADS) sh[i] = 0;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	u32* sh = reinterpret_cast<u32*>(smem_raw);          /* [PASSES][RADIX][COLS] */
+	for (int i = threadIdx.x; i < PASSES * RADIX * COLS; i += THREADS) sh[i] = 0;
 	__syncthreads();
+	const u32 col = threadIdx.x & (COLS - 1);
+	u32 sb[PASSES], dm[PASSES];
+#pragma unroll
+	for (int p = 0; p < PASSES; ++p) { sb[p] = cfg.start_bit[p]; dm[p] = cfg.dmask[p]; }
+	auto count = [&](ElemT e) {
+		const u64 k = radix_key<ElemT, IDENTITY>(e, ks);
+#pragma unroll
+		for (int p = 0; p < PASSES; ++p) {
+			const u32 d = (sizeof(ElemT) <= 4 && IDENTITY) ? (((u32) k >> sb[p]) & dm[p]) : ((u32) (k >> sb[p]) & dm[p]);
+			atomicAdd(&sh[(p * RADIX + d) * COLS + col], 1u);
+		}
+	};
 	constexpr int EPV = 16 / sizeof(ElemT);
 	const size_t stride = (size_t) gridDim.x * THREADS;
 	const size_t tid = (size_t) blockIdx.x * THREADS + threadIdx.x;
 	if (vec_ok) {
 		const size_t nvec = n / EPV;
-		for (size_t i = tid; i < nvec; i += stride) {
-			ElemT e[EPV];
-			load_vec_cs<ElemT, EPV>(in + i * EPV, e);
+		size_t i = tid;
+		/* two vectors in flight per thread */
+		for (; i + stride < nvec; i += 2 * stride) {
+			ElemT e0[EPV], e1[EPV];
+			load_vec_cs<ElemT, EPV>(in + i * EPV, e0);
+			load_vec_cs<ElemT, EPV>(in + (i + stride) * EPV, e1);
 #pragma unroll
-			for (int c = 0; c < EPV; ++c) {
-				const u64 k = radix_key<ElemT, IDENTITY>(e[c], ks);
-				for (int p = 0; p < cfg.passes; ++p)
-					atomicAdd(&sh[p * RADIX + ((u32) (k >> cfg.start_bit[p]) & cfg.dmask[p])], 1u);
-			}
+			for (int c = 0; c < EPV; ++c) count(e0[c]);
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) count(e1[c]);
 		}
-		for (size_t i = nvec * EPV + tid; i < n; i += stride) {
-			const u64 k = radix_key<ElemT, IDENTITY>(in[i], ks);
-			for (int p = 0; p < cfg.passes; ++p)
-				atomicAdd(&sh[p * RADIX + ((u32) (k >> cfg.start_bit[p]) & cfg.dmask[p])], 1u);
+		for (; i < nvec; i += stride) {
+			ElemT e0[EPV];
+			load_vec_cs<ElemT, EPV>(in + i * EPV, e0);
+#pragma unroll
+			for (int c = 0; c < EPV; ++c) count(e0[c]);
 		}
+		for (size_t r = nvec * EPV + tid; r < n; r += stride) count(in[r]);
 	} else {
-		for (size_t i = tid; i < n; i += stride) {
-			const u64 k = radix_key<ElemT, IDENTITY>(in[i], ks);
-			for (int p = 0; p < cfg.passes; ++p)
-				atomicAdd(&sh[p * RADIX + ((u32) (k >> cfg.start_bit[p]) & cfg.dmask[p])], 1u);
-		}
+		for (size_t r = tid; r < n; r += stride) count(in[r]);
 	}
 	__syncthreads();
-	for (int i = threadIdx.x; i < cfg.passes * RADIX; i += THREADS) {
-		const u32 c = sh[i];
-		if (c) atomicAdd(&ghist[i], (u64) c);
+	/* fold the columns (rotated start: conflict free) and add to the global histogram */
+	for (int b = threadIdx.x; b < PASSES * RADIX; b += THREADS) {
+		u32 t = 0;
+#pragma unroll 8
+		for (int c = 0; c < COLS; ++c) t += sh[b * COLS + ((c + threadIdx.x) & (COLS - 1))];
+		if (t) atomicAdd(&ghist[b], (u64) t);
 	}
 }
 
@@ -178,15 +201,18 @@ struct SplitterArgs {
 enum { RANK_BALLOT = 0, RANK_ATOMIC = 1 };
 
 template <typename ElemT, bool HAS_VAL, bool IDENTITY, bool PARTITION, typename LbT,
-	int THREADS, int IPT, int RANK_MODE>
+	int THREADS, int IPT, int RANK_MODE, int LBF = LB_FIRST, int LBN = LB_NEXT>
 __global__ void __launch_bounds__(THREADS, (THREADS >= 384 ? 2 : 4))
 clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
 		LbT* __restrict__ lookback, u32* __restrict__ ticket, const u64* __restrict__ bins_base,
-		u32 start_bit, u32 dmask, CloKeySpec ks, SplitterArgs sp, int* __restrict__ err_flag) {
+		u32 start_bit, u32 dmask, CloKeySpec ks, SplitterArgs sp, int* __restrict__ err_flag, int prof_on) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int TILE = THREADS * IPT;
 	constexpr bool VERIFY = (RANK_MODE == RANK_ATOMIC);
+	/* the (digit, index) word is needed whenever the key alone cannot prove stability or
+	 * give the digit back: payloads, extracted keys, the splitter partition */
+	constexpr bool USE_INFO = HAS_VAL || !IDENTITY || PARTITION;
 	static_assert(THREADS >= RADIX, "one thread per digit is needed");
 	static_assert(TILE <= 65536, "index-in-tile must fit 16 bits");
 
@@ -196,221 +222,298 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	LbT* s_goff = reinterpret_cast<LbT*>(s_dstart + RADIX);                /* [RADIX] (u64-sized slot) */
 	u32* s_misc = s_dstart + RADIX + 2 * RADIX;                            /* [16]: tile, warp sums, flags */
 	ElemT* skeys = reinterpret_cast<ElemT*>(s_misc + 16);                  /* [TILE] */
-	u32* sinfo = reinterpret_cast<u32*>(skeys + TILE);                     /* [TILE] digit<<16 | index */
-	u32* svals = sinfo + TILE;                                             /* [TILE] if HAS_VAL */
+	u32* sinfo = reinterpret_cast<u32*>(skeys + TILE);                     /* [TILE] digit<<16 | index, if USE_INFO */
+	u32* svals = sinfo + TILE;                                             /* [TILE] if HAS_VAL (then USE_INFO) */
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	/* bits of this digit and below (keys-only verification) */
+	const ElemT low_mask = (ElemT) ((((ElemT) dmask) << start_bit) | ((((ElemT) 1) << start_bit) - 1));
+
+	/* optional phase profile (CLO_RADIX_PROFILE=1): thread 0 accumulates cycles per phase
+	 * into the u64 counters behind the status words */
+	long long t_prev = 0;
+	u64* prof = reinterpret_cast<u64*>(err_flag + 16);
+	auto mark = [&](int phase) {
+		if (prof_on && tid == 0) {
+			const long long t = clock64();
+			atomicAdd(prof + phase, (u64) (t - t_prev));
+			t_prev = t;
+		}
+	};
+	if (prof_on && tid == 0) t_prev = clock64();
 
 	if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
 	for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
 	__syncthreads();
+	mark(0);
 	const u32 tile = s_misc[0];
 	const size_t tile_base = (size_t) tile * TILE;
 	const bool full = tile_base + TILE <= n;
 	const u32 tile_count = full ? (u32) TILE : (u32) (n - tile_base);
 
-	/* ---- load, warp-striped: item i of lane l is element warp*32*IPT + i*32 + l */
-	ElemT key[IPT];
-	u32 val[HAS_VAL ? IPT : 1];
-	u32 pos[IPT];
-	const u32 wbase = (u32) warp * 32u * IPT + lane;
+	/* The whole tile body is instantiated twice, for full tiles (no per-item bounds
+	 * checks at all) and for the single partial tile at the end. */
+	auto body = [&](auto full_tag) {
+		constexpr bool FULL = decltype(full_tag)::value;
+		/* ---- load, warp-striped: item i of lane l is element warp*32*IPT + i*32 + l */
+		ElemT key[IPT];
+		u32 val[HAS_VAL ? IPT : 1];
+		u32 pos2[(IPT + 1) / 2];   /* ranks, two 16-bit halves per register */
 #pragma unroll
-	for (int i = 0; i < IPT; ++i) {
-		const u32 local = wbase + i * 32u;
-		if (full || local < tile_count) {
-			key[i] = __ldcs(in + tile_base + local);
-			if (HAS_VAL) val[i] = __ldcs(vin + tile_base + local);
-		} else {
-			key[i] = ElemT(0);
-			if (HAS_VAL) val[i] = 0;
+		for (int i = 0; i < (IPT + 1) / 2; ++i) pos2[i] = 0;
+		const u32 wbase = (u32) warp * 32u * IPT + lane;
+	#pragma unroll
+		for (int i = 0; i < IPT; ++i) {
+			const u32 local = wbase + i * 32u;
+			if (FULL || local < tile_count) {
+				key[i] = __ldcs(in + tile_base + local);
+				if (HAS_VAL) val[i] = __ldcs(vin + tile_base + local);
+			} else {
+				key[i] = ElemT(0);
+				if (HAS_VAL) val[i] = 0;
+			}
 		}
-	}
 
-	/* splitter table for the partition variant (tiny: <= 15 entries) */
-	ElemT sp_key[PARTITION ? 15 : 1];
-	u64 sp_idx[PARTITION ? 15 : 1];
-	if (PARTITION) {
-#pragma unroll
-		for (int s = 0; s < 15; ++s) {
-			if (s < (int) sp.count) {
-				sp_key[s] = reinterpret_cast<const ElemT*>(sp.keys)[s];
-				sp_idx[s] = sp.idx[s];
-			} else { sp_key[s] = ElemT(0); sp_idx[s] = 0; }
-		}
-	}
-
-	auto digit_of = [&](ElemT k, u32 local) -> u32 {
+		/* splitter table for the partition variant (tiny: <= 15 entries) */
+		ElemT sp_key[PARTITION ? 15 : 1];
+		u64 sp_idx[PARTITION ? 15 : 1];
 		if (PARTITION) {
-			const u64 g = sp.gidx0 + tile_base + local;
-			u32 b = 0;
-#pragma unroll
-			for (int s = 0; s < 15; ++s)
-				if (s < (int) sp.count && (sp_key[s] < k || (sp_key[s] == k && sp_idx[s] <= g))) ++b;
-			return b;
-		}
-		return radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
-	};
-
-	u32* wh = whist + warp * RADIX;
-
-	/* ---- rank inside the warp: pos[i] = number of earlier keys of this warp with my digit;
-	 *      afterwards wh[d] = number of keys of this warp with digit d */
-	auto rank_ballot = [&]() {
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 local = wbase + i * 32u;
-			const bool valid = full || local < tile_count;
-			const u32 d = digit_of(key[i], local);
-			u32 peers = match_digit_ballot(d);
-			if (!full) peers &= __ballot_sync(0xffffffffu, valid);
-			const u32 lt = peers & lanemask_lt();
-			u32 old = 0;
-			if (valid && lt == 0) {            /* first lane of its digit group */
-				old = wh[d];
-				wh[d] = old + __popc(peers);
-			}
-			__syncwarp();
-			const int leader = __ffs(peers) - 1;
-			old = __shfl_sync(0xffffffffu, old, leader & 31);
-			pos[i] = old + __popc(lt);
-		}
-	};
-	auto rank_atomic = [&]() {
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 local = wbase + i * 32u;
-			if (full || local < tile_count) pos[i] = atomicAdd(&wh[digit_of(key[i], local)], 1u);
-		}
-	};
-
-	/* ---- per digit (thread d): exclusive offsets of the warps, tile count */
-	auto digit_count = [&]() -> u32 {
-		u32 count = 0;
-		if (tid < RADIX) {
-#pragma unroll
-			for (int w = 0; w < WARPS; ++w) {
-				const u32 c = whist[w * RADIX + tid];
-				whist[w * RADIX + tid] = count;
-				count += c;
+	#pragma unroll
+			for (int s = 0; s < 15; ++s) {
+				if (s < (int) sp.count) {
+					sp_key[s] = reinterpret_cast<const ElemT*>(sp.keys)[s];
+					sp_idx[s] = sp.idx[s];
+				} else { sp_key[s] = ElemT(0); sp_idx[s] = 0; }
 			}
 		}
-		return count;
-	};
-	/* exclusive scan of the 256 counts -> start of each digit inside the tile, folded into
-	 * the per-warp offsets so that staging needs one table lookup (contains a barrier) */
-	auto digit_starts = [&](u32 count) {
-		const u32 incl = warp_inclusive_scan<u32>(count, lane);
-		if (tid < RADIX && lane == 31) s_misc[1 + warp] = incl;
-		__syncthreads();
-		if (tid < RADIX) {
-			u32 off = 0;
-#pragma unroll
-			for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[1 + w];
-			const u32 ds = off + incl - count;
-			s_dstart[tid] = ds;
-#pragma unroll
-			for (int w = 0; w < WARPS; ++w) whist[w * RADIX + tid] += ds;
-		}
-	};
-	/* ---- stage the tile in digit order */
-	auto stage = [&]() {
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 local = wbase + i * 32u;
-			if (full || local < tile_count) {
+
+		auto digit_of = [&](ElemT k, u32 local) -> u32 {
+			if (PARTITION) {
+				const u64 g = sp.gidx0 + tile_base + local;
+				u32 b = 0;
+	#pragma unroll
+				for (int s = 0; s < 15; ++s)
+					if (s < (int) sp.count && (sp_key[s] < k || (sp_key[s] == k && sp_idx[s] <= g))) ++b;
+				return b;
+			}
+			return radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
+		};
+
+		u32* wh = whist + warp * RADIX;
+
+		/* ---- rank inside the warp: pos[i] = number of earlier keys of this warp with my digit;
+		 *      afterwards wh[d] = number of keys of this warp with digit d */
+		auto rank_ballot = [&]() {
+	#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				const u32 local = wbase + i * 32u;
+				const bool valid = FULL || local < tile_count;
 				const u32 d = digit_of(key[i], local);
-				const u32 p = wh[d] + pos[i];
-				skeys[p] = key[i];
-				sinfo[p] = (d << 16) | local;
-				if (HAS_VAL) svals[p] = val[i];
+				u32 peers = match_digit_ballot(d);
+				if (!FULL) peers &= __ballot_sync(0xffffffffu, valid);
+				const u32 lt = peers & lanemask_lt();
+				u32 old = 0;
+				if (valid && lt == 0) {            /* first lane of its digit group */
+					old = wh[d];
+					wh[d] = old + __popc(peers);
+				}
+				__syncwarp();
+				const int leader = __ffs(peers) - 1;
+				old = __shfl_sync(0xffffffffu, old, leader & 31);
+				pos2[i >> 1] |= (old + __popc(lt)) << (16 * (i & 1));
 			}
-		}
-	};
-	/* ---- write out: element j of the staged tile -> goff[digit] + j.  Returns whether
-	 *      the staged order was seen to be unstable (VERIFY only). */
-	auto write_out = [&](bool verify) -> bool {
-		bool bad = false;
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 j = (u32) tid + i * THREADS;
-			if (full || j < tile_count) {
-				const u32 info = sinfo[j];
-				if (verify && j > 0 && info <= sinfo[j - 1]) bad = true;
-				const LbT o = s_goff[info >> 16] + (LbT) j;
-				out[o] = skeys[j];
-				if (HAS_VAL) vout[o] = svals[j];
+		};
+		auto rank_atomic = [&]() {
+	#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				const u32 local = wbase + i * 32u;
+				if (FULL || local < tile_count)
+					pos2[i >> 1] |= atomicAdd(&wh[digit_of(key[i], local)], 1u) << (16 * (i & 1));
 			}
-		}
-		return bad;
-	};
+		};
 
-	if (RANK_MODE == RANK_ATOMIC) rank_atomic(); else rank_ballot();
-	__syncthreads();
-
-	const u32 count = digit_count();
-	/* publish the tile aggregate as early as possible */
-	LbT* lb_mine = lookback + (size_t) tile * RADIX;
-	if (tid < RADIX) {
-		if (tile == 0) st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | (LbT) count));
-		else st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::AGG | (LbT) count));
-	}
-	digit_starts(count);
-
-	/* ---- decoupled look-back, one digit per thread */
-	if (tid < RADIX) {
-		LbT excl = 0;
-		if (tile > 0) {
-			long long p = (long long) tile - 1;
-			unsigned spins = 0;
-			bool done = false;
-			while (!done) {
-				/* LB_BATCH predecessor words in flight at once; consumed nearest first */
-				LbT w[LB_BATCH];
+		/* ---- per digit (thread d): tile count = sum of the warps' counts (independent loads) */
+		auto digit_count = [&]() -> u32 {
+			u32 count = 0;
+			if (tid < RADIX) {
 #pragma unroll
-				for (int k = 0; k < LB_BATCH; ++k)
-					w[k] = (p - k >= 0) ? ld_relaxed(lookback + (size_t) (p - k) * RADIX + tid) : (LbT) Lb<LbT>::PREFIX;
+				for (int w = 0; w < WARPS; ++w) count += whist[w * RADIX + tid];
+			}
+			return count;
+		};
+		/* exclusive scan of the 256 counts -> start of each digit inside the tile; the per-warp
+		 * counts become dstart[d] + (count of d in lower warps), so staging needs one lookup.
+		 * Contains a barrier. */
+		auto digit_starts = [&](u32 count) {
+			const u32 incl = warp_inclusive_scan<u32>(count, lane);
+			if (tid < RADIX && lane == 31) s_misc[1 + warp] = incl;
+			__syncthreads();
+			if (tid < RADIX) {
+				u32 off = 0;
 #pragma unroll
-				for (int k = 0; k < LB_BATCH; ++k) {
-					if (!done) {
-						const LbT f = w[k] & Lb<LbT>::FLAGS;
-						if (f == 0) {            /* not published yet: retry from here */
-							if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); done = true; }
-							break;
-						}
-						excl += w[k] & Lb<LbT>::VAL;
-						--p;
-						if (f == Lb<LbT>::PREFIX) done = true;
-					}
+				for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[1 + w];
+				const u32 ds = off + incl - count;
+				s_dstart[tid] = ds;
+				u32 c[WARPS];
+#pragma unroll
+				for (int w = 0; w < WARPS; ++w) c[w] = whist[w * RADIX + tid];
+				u32 run = ds;
+#pragma unroll
+				for (int w = 0; w < WARPS; ++w) { whist[w * RADIX + tid] = run; run += c[w]; }
+			}
+		};
+		/* ---- stage the tile in digit order.  VERIFY_KEYS (keys only, identity key): the keys
+		 *      themselves prove a correct pass, nothing else is staged.  Otherwise the
+		 *      (digit, index-in-tile) word is staged beside the key. */
+		auto stage = [&]() {
+#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				const u32 local = wbase + i * 32u;
+				if (FULL || local < tile_count) {
+					const u32 d = digit_of(key[i], local);
+					const u32 p = wh[d] + ((pos2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
+					skeys[p] = key[i];
+					if (USE_INFO) sinfo[p] = (d << 16) | local;
+					if (HAS_VAL) svals[p] = val[i];
 				}
 			}
-			st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | ((excl + count) & Lb<LbT>::VAL)));
-		}
-		/* modular arithmetic in LbT: the final index goff[d] + j is < n */
-		s_goff[tid] = (LbT) bins_base[tid] + excl - (LbT) s_dstart[tid];
-	}
-	__syncthreads();
+		};
+		/* ---- write out: element j of the staged tile -> goff[digit] + j.  Returns whether the
+		 *      staged order was seen to violate the pass invariant:
+		 *      with the info word: (digit, index-in-tile) strictly increasing == stable;
+		 *      keys only: the input of pass p is sorted on the bits below start_bit, so the
+		 *      output is correct iff (key & low_mask) is non-decreasing along the staged tile,
+		 *      low_mask covering this digit and everything below it. */
+		auto write_out = [&](bool verify) -> bool {
+			bool bad = false;
+#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				const u32 j = (u32) tid + i * THREADS;
+				if (FULL || j < tile_count) {
+					const ElemT k = skeys[j];
+					u32 d;
+					if (USE_INFO) {
+						const u32 info = sinfo[j];
+						if (verify && j > 0 && info <= sinfo[j - 1]) bad = true;
+						d = info >> 16;
+					} else {
+						if (verify && j > 0 && (k & low_mask) < (skeys[j - 1] & low_mask)) bad = true;
+						d = radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
+					}
+					const LbT o = s_goff[d] + (LbT) j;
+					out[o] = k;
+					if (HAS_VAL) vout[o] = svals[j];
+				}
+			}
+			return bad;
+		};
 
-	stage();
-	__syncthreads();
-	const bool bad = write_out(VERIFY);
+		if (prof_on) { if (tid == 0 && key[IPT - 1] == ElemT(0x5a5a5a5a)) prof[15] = 1; mark(1); }  /* loads landed */
+		if (RANK_MODE == RANK_ATOMIC) rank_atomic(); else rank_ballot();
+		__syncthreads();
+		mark(2);
 
-	if (VERIFY) {
-		if (__syncthreads_or(bad ? 1 : 0)) {
-			/* The atomic ranks were not in lane order somewhere in this tile: redo the tile
-			 * with the ballot ranks.  Digit counts, hence every offset, are unchanged. */
-			if (tid == 0) atomicAdd(err_flag + 1, 1);
-			for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
-			__syncthreads();
-			rank_ballot();
-			__syncthreads();
-			const u32 count2 = digit_count();
-			digit_starts(count2);
-			__syncthreads();
-			stage();
-			__syncthreads();
-			write_out(false);
+		const u32 count = digit_count();
+		/* publish the tile aggregate as early as possible */
+		LbT* lb_mine = lookback + (size_t) tile * RADIX;
+		if (tid < RADIX) {
+			if (tile == 0) st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | (LbT) count));
+			else st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::AGG | (LbT) count));
 		}
-	}
+		digit_starts(count);
+		__syncthreads();
+		mark(3);
+
+		/* Staging needs tile-local offsets only.  The warps that own a digit (tid < RADIX)
+		 * resolve their look-back first -- so the tile's inclusive prefix is published as
+		 * early as possible, which keeps every successor's walk short -- while the other
+		 * warps already stage their keys. */
+		/* ---- decoupled look-back, one digit per thread */
+		auto look_back = [&]() {
+			LbT excl = 0;
+			if (tile > 0) {
+				long long p = (long long) tile - 1;
+				unsigned spins = 0;
+				bool done = false;
+				/* A window of predecessor words is loaded at once (all loads in flight
+				 * together) and consumed nearest first.  While tiles wait here, their
+				 * successors must walk over them, so a short window makes the backlog --
+				 * and with it every walk -- longer; after a first small window the walk
+				 * continues with wide ones. */
+				auto walk = [&](auto batch_tag) {
+					constexpr int B = decltype(batch_tag)::value;
+					LbT w[B];
+#pragma unroll
+					for (int k = 0; k < B; ++k)
+						w[k] = (p - k >= 0) ? ld_relaxed(lookback + (size_t) (p - k) * RADIX + tid) : (LbT) Lb<LbT>::PREFIX;
+#pragma unroll
+					for (int k = 0; k < B; ++k) {
+						if (!done) {
+							const LbT f = w[k] & Lb<LbT>::FLAGS;
+							if (f == 0) {            /* not published yet: retry from here */
+								if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); done = true; }
+								break;
+							}
+							excl += w[k] & Lb<LbT>::VAL;
+							--p;
+							if (f == Lb<LbT>::PREFIX) done = true;
+						}
+					}
+				};
+				const long long lb_t0 = prof_on ? clock64() : 0;
+				u32 rounds = 1;
+				walk(std::integral_constant<int, LBF>{});
+				while (!done) { walk(std::integral_constant<int, LBN>{}); ++rounds; }
+				if (prof_on && tid == 0) {
+					atomicAdd(prof + 7, (u64) (clock64() - lb_t0));   /* cycles inside the walk */
+					atomicAdd(prof + 8, (u64) rounds);                  /* window loads */
+					atomicAdd(prof + 9, (u64) spins);                   /* unpublished words met */
+					atomicAdd(prof + 10, (u64) ((long long) tile - 1 - p));  /* predecessors consumed */
+				}
+				st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | ((excl + count) & Lb<LbT>::VAL)));
+			}
+			/* modular arithmetic in LbT: the final index goff[d] + j is < n */
+			s_goff[tid] = (LbT) bins_base[tid] + excl - (LbT) s_dstart[tid];
+		};
+		if (tid < RADIX) look_back();
+		stage();
+		mark(4);
+		__syncthreads();
+		mark(5);
+
+		const bool bad = write_out(VERIFY);
+		mark(6);
+
+		if (VERIFY) {
+			if (__syncthreads_or(bad ? 1 : 0)) {
+				/* The atomic ranks were not in lane order somewhere in this tile: redo the tile
+				 * with the ballot ranks.  Digit counts, hence every offset, are unchanged. */
+				if (tid == 0) atomicAdd(err_flag + 1, 1);
+				for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
+				__syncthreads();
+#pragma unroll
+				for (int i = 0; i < (IPT + 1) / 2; ++i) pos2[i] = 0;
+				/* keys (and payloads) are re-read: their registers were released after staging */
+#pragma unroll
+				for (int i = 0; i < IPT; ++i) {
+					const u32 local = wbase + i * 32u;
+					if (FULL || local < tile_count) {
+						key[i] = in[tile_base + local];
+						if (HAS_VAL) val[i] = vin[tile_base + local];
+					}
+				}
+				rank_ballot();
+				__syncthreads();
+				const u32 count2 = digit_count();
+				digit_starts(count2);
+				__syncthreads();
+				stage();
+				__syncthreads();
+				write_out(false);
+			}
+		}
+	};
+	if (full) body(std::true_type{}); else body(std::false_type{});
 }
 
 /* ------------------------------------------------------------- host side */
@@ -421,10 +524,10 @@ template <typename ElemT, bool HAS_VAL> struct TileCfg {
 	static const int IPT = HAS_VAL ? (sizeof(ElemT) == 8 ? 8 : 12) : (sizeof(ElemT) == 8 ? 8 : 16);
 };
 
-template <typename ElemT, bool HAS_VAL, int THREADS, int IPT>
+template <typename ElemT, bool HAS_VAL, int THREADS, int IPT, bool USE_INFO = true>
 constexpr size_t onesweep_smem() {
 	return (size_t) (THREADS / 32) * RADIX * 4 + RADIX * 4 + RADIX * 8 + 16 * 4 +
-		(size_t) THREADS * IPT * sizeof(ElemT) + (size_t) THREADS * IPT * 4 +
+		(size_t) THREADS * IPT * sizeof(ElemT) + (USE_INFO || HAS_VAL ? (size_t) THREADS * IPT * 4 : 0) +
 		(HAS_VAL ? (size_t) THREADS * IPT * 4 : 0);
 }
 
@@ -436,21 +539,58 @@ struct CloRadixState {
 	CloScratch work;         /* [err | ghist | bins_base | tickets | lookback...] */
 	int rank_atomic = 1;     /* CLO_RADIX_RANK=ballot selects the ballot ranks */
 	int cfg = 0;
+	/* optional per-kernel timing of the last call (clo_radix_set_timing) */
+	int timing = 0;
+	int n_marks = 0;
+	cudaEvent_t marks[2 + MAX_PASSES + 2] = {};
+	void mark(cudaStream_t stream) {
+		if (!timing || n_marks >= (int) (sizeof(marks) / sizeof(marks[0]))) return;
+		if (!marks[n_marks]) cudaEventCreate(&marks[n_marks]);
+		cudaEventRecord(marks[n_marks++], stream);
+	}
 };
 
 CloRadixState* clo_radix_state_new() {
 	CloRadixState* st = new CloRadixState();
 	const char* e = getenv("CLO_RADIX_RANK");
 	st->rank_atomic = (e && strcmp(e, "ballot") == 0) ? 0 : 1;
+	const char* pf = getenv("CLO_RADIX_PROFILE");
+	g_radix_profile = (pf && *pf == '1') ? 1 : 0;
 	const char* c = getenv("CLO_RADIX_CFG");
 	st->cfg = (c && *c) ? atoi(c) : 0;
 	return st;
 }
 
+void clo_radix_set_timing(CloRadixState* st, int on) { if (st) st->timing = on; }
+
+/* durations (ms) of the last call: out[0] = histogram + bin scan, out[1..passes] = the
+ * onesweep passes; returns the number of values, 0 when timing was off */
+int clo_radix_get_timing(CloRadixState* st, float* out, int cap) {
+	if (!st || st->n_marks < 2) return 0;
+	if (cudaEventSynchronize(st->marks[st->n_marks - 1]) != cudaSuccess) return 0;
+	int k = 0;
+	for (int i = 0; i + 1 < st->n_marks && k < cap; ++i, ++k)
+		if (cudaEventElapsedTime(&out[k], st->marks[i], st->marks[i + 1]) != cudaSuccess) return 0;
+	return k;
+}
+
 void clo_radix_state_free(CloRadixState* st) {
 	if (!st) return;
+	for (cudaEvent_t e : st->marks) if (e) cudaEventDestroy(e);
 	st->aux_keys.release(); st->aux_vals.release(); st->work.release();
 	delete st;
+}
+
+int clo_radix_debug(CloRadixState* st, cudaStream_t stream, unsigned long long out[18]) {
+	for (int i = 0; i < 18; ++i) out[i] = 0;
+	if (!st || !st->work.ptr) return 0;
+	int hdr[64];
+	if (cudaMemcpyAsync(hdr, st->work.ptr, sizeof(hdr), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return -1;
+	if (cudaStreamSynchronize(stream) != cudaSuccess) return -1;
+	out[0] = (unsigned long long) hdr[0];
+	out[1] = (unsigned long long) hdr[1];
+	memcpy(out + 2, hdr + 16, 16 * sizeof(unsigned long long));
+	return 0;
 }
 
 int clo_radix_status(CloRadixState* st, cudaStream_t stream) {
@@ -487,12 +627,12 @@ cudaError_t prepare_work(CloRadixState* st, size_t tiles, int passes, size_t lb_
 	return cudaMemsetAsync(base, 0, L.zero_bytes, stream);
 }
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int RANK_MODE, int THREADS, int IPT>
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int RANK_MODE, int THREADS, int IPT, int LBF = LB_FIRST, int LBN = LB_NEXT>
 cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n,
 		LbT* lookback, u32* ticket, const u64* bins, u32 start_bit, u32 dmask, const CloKeySpec& ks,
 		int* err, cudaStream_t stream) {
-	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT>();
-	auto kern = clo_radix_onesweep<ElemT, HAS_VAL, IDENTITY, false, LbT, THREADS, IPT, RANK_MODE>;
+	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT, (HAS_VAL || !IDENTITY)>();
+	auto kern = clo_radix_onesweep<ElemT, HAS_VAL, IDENTITY, false, LbT, THREADS, IPT, RANK_MODE, LBF, LBN>;
 	static bool configured[64] = {};
 	int dev = 0;
 	cudaGetDevice(&dev);
@@ -504,12 +644,38 @@ cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vo
 	const size_t tiles = (n + (size_t) THREADS * IPT - 1) / ((size_t) THREADS * IPT);
 	SplitterArgs sp = { nullptr, nullptr, 0, 0 };
 	kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, lookback, ticket, bins,
-		start_bit, dmask, ks, sp, err);
+		start_bit, dmask, ks, sp, err, g_radix_profile);
 	CLO_COUNT_LAUNCH(1);
 	return cudaGetLastError();
 }
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY, int THREADS, int IPT>
+template <typename ElemT, bool IDENTITY, int PASSES, int COLS>
+cudaError_t launch_histogram_p(const ElemT* src, size_t n, u64* ghist, const PassCfg& cfg, const CloKeySpec& ks,
+		int vec_ok, int sm_count, cudaStream_t stream) {
+	constexpr int THREADS = 1024;
+	constexpr size_t SMEM = (size_t) PASSES * RADIX * COLS * sizeof(u32);
+	auto kern = clo_radix_histogram<ElemT, IDENTITY, PASSES, COLS, THREADS>;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM);
+	if (e != cudaSuccess) return e;
+	size_t want = (n + (size_t) THREADS * 16 - 1) / ((size_t) THREADS * 16);
+	const unsigned blocks = (unsigned) (want < (size_t) sm_count ? (want ? want : 1) : (size_t) sm_count);
+	kern<<<blocks, THREADS, SMEM, stream>>>(src, n, ghist, cfg, ks, vec_ok);
+	return cudaGetLastError();
+}
+
+template <typename ElemT, bool IDENTITY>
+cudaError_t launch_histogram(const ElemT* src, size_t n, u64* ghist, const PassCfg& cfg, const CloKeySpec& ks,
+		int vec_ok, int sm_count, cudaStream_t stream) {
+	/* 32 columns (conflict free) up to 4 passes = 128 KB; 16 columns for 5..8 passes */
+	switch (cfg.passes) {
+	case 1: return launch_histogram_p<ElemT, IDENTITY, 1, 32>(src, n, ghist, cfg, ks, vec_ok, sm_count, stream);
+	case 2: return launch_histogram_p<ElemT, IDENTITY, 2, 32>(src, n, ghist, cfg, ks, vec_ok, sm_count, stream);
+	case 3: case 4: return launch_histogram_p<ElemT, IDENTITY, 4, 32>(src, n, ghist, cfg, ks, vec_ok, sm_count, stream);
+	default: return launch_histogram_p<ElemT, IDENTITY, 8, 16>(src, n, ghist, cfg, ks, vec_ok, sm_count, stream);
+	}
+}
+
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, int THREADS, int IPT, int LBF = LB_FIRST, int LBN = LB_NEXT>
 cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
 		const ElemT* src, ElemT* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
 	constexpr size_t TILE = (size_t) THREADS * IPT;
@@ -531,17 +697,17 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 	ElemT* aux = (ElemT*) st->aux_keys.ptr;
 	u32* vaux = (u32*) st->aux_vals.ptr;
 
-	/* histogram of every digit in one read of the keys */
+	st->n_marks = 0;
+	st->mark(stream);
+	/* histogram of every digit in one read of the keys: one persistent CTA per SM */
 	{
 		const int vec_ok = (reinterpret_cast<uintptr_t>(src) % 16) == 0;
-		size_t want = (n + 256 * 16 - 1) / (256 * 16);
-		size_t cap = (size_t) sm_count * 8;
-		const unsigned blocks = (unsigned) (want < cap ? (want ? want : 1) : cap);
-		clo_radix_histogram<ElemT, IDENTITY, 256><<<blocks, 256, 0, stream>>>(src, n, L.ghist, cfg, ks, vec_ok);
+		if ((e = launch_histogram<ElemT, IDENTITY>(src, n, L.ghist, cfg, ks, vec_ok, sm_count, stream)) != cudaSuccess) return e;
 		clo_radix_scan_bins<<<cfg.passes, RADIX, 0, stream>>>(L.ghist, L.bins);
 		CLO_COUNT_LAUNCH(2);
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	}
+	st->mark(stream);
 
 	/* ping-pong chain that ends in dst without touching src (unless in place):
 	 * odd number of passes: src->dst->aux->dst...; even: src->aux->dst->aux->dst */
@@ -563,15 +729,16 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		if (wide) {
 			u64* lb = (u64*) L.lookback + (size_t) p * tiles * RADIX;
 			e = st->rank_atomic
-				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
-				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 1, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
+				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		} else {
 			u32* lb = (u32*) L.lookback + (size_t) p * tiles * RADIX;
 			e = st->rank_atomic
-				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
-				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 1, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
+				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		}
 		if (e != cudaSuccess) return e;
+		st->mark(stream);
 		cur = nxt; vcur = vnxt;
 	}
 	return cudaSuccess;
@@ -594,6 +761,10 @@ cudaError_t radix_sort_typed<u32, false, true>(CloRadixState* st, int sm_count, 
 	case 2: return radix_sort_cfg<u32, false, true, 384, 18>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	case 3: return radix_sort_cfg<u32, false, true, 256, 12>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	case 4: return radix_sort_cfg<u32, false, true, 512, 12>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 5: return radix_sort_cfg<u32, false, true, 512, 16, 16, 32>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 6: return radix_sort_cfg<u32, false, true, 512, 16, 32, 32>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 7: return radix_sort_cfg<u32, false, true, 512, 16, 48, 32>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	case 8: return radix_sort_cfg<u32, false, true, 512, 16, 4, 4>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	default: return radix_sort_cfg<u32, false, true, 512, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 	}
 }
@@ -708,11 +879,11 @@ cudaError_t partition_typed(CloRadixState* st, const ElemT* in, const u32* vin, 
 	if (wide) {
 		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u64, THREADS, IPT, RANK_BALLOT>;
 		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
-		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u64*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err);
+		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u64*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err, 0);
 	} else {
 		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u32, THREADS, IPT, RANK_BALLOT>;
 		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
-		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u32*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err);
+		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u32*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err, 0);
 	}
 	CLO_COUNT_LAUNCH(1);
 	return cudaGetLastError();

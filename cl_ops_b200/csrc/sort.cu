@@ -535,6 +535,26 @@ extern "C" size_t clo_sort_get_localmem_usage(CloSort* s, cl_uint i, size_t lws_
 
 /* ------------------------------------------------ additive entry points */
 
+extern "C" void clo_sort_b200_set_timing(CloSort* sorter, cl_bool on) {
+	if (sorter) clo_radix_set_timing(sorter->rs, on ? 1 : 0);
+}
+
+extern "C" cl_uint clo_sort_b200_get_timing(CloSort* sorter, float* out_ms, cl_uint cap) {
+	if (!sorter || !out_ms) return 0;
+	CloDeviceGuard g(sorter->ctx->dev.ordinal);
+	return (cl_uint) clo_radix_get_timing(sorter->rs, out_ms, (int) cap);
+}
+
+extern "C" cl_bool clo_sort_b200_debug(CloSort* sorter, CCLQueue* cq, cl_ulong out[18]) {
+	if (!sorter || !cq || !out) return CL_FALSE;
+	CloDeviceGuard g(cq->ctx->dev.ordinal);
+	unsigned long long tmp[18];
+	if (clo_radix_debug(sorter->rs, cq->stream, tmp) != 0) return CL_FALSE;
+	for (int i = 0; i < 18; ++i) out[i] = tmp[i];
+	return CL_TRUE;
+}
+
+
 extern "C" CCLEvent* clo_sort_pairs_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
 		CCLBuffer* keys, CCLBuffer* payload, size_t numel, GError** err) {
 	if (!sorter || (err && *err) || !cq_exec) return NULL;

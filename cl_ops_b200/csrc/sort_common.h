@@ -75,6 +75,14 @@ cudaError_t clo_radix_partition(CloRadixState* st, size_t elem_size, const void*
 	const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out,
 	cudaStream_t stream, const char** err_msg);
 
+/* status words of the last radix call: [0] look-back timeout flag, [1] tiles repaired by
+ * the ballot path, [2..17] phase-profile cycle counters; synchronises the stream */
+int clo_radix_debug(CloRadixState* st, cudaStream_t stream, unsigned long long out[18]);
+
+/* per-kernel CUDA-event timing of the radix calls (bench evidence) */
+void clo_radix_set_timing(CloRadixState* st, int on);
+int clo_radix_get_timing(CloRadixState* st, float* out_ms, int cap);
+
 /* device status flag of the last radix call (0 = ok); synchronises the stream */
 int clo_radix_status(CloRadixState* st, cudaStream_t stream);
 

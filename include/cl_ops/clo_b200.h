@@ -61,6 +61,18 @@ CCLEvent* clo_sort_partition_with_device_data(CloSort* sorter, CCLQueue* cq_exec
 	CCLBuffer* splitter_keys, CCLBuffer* splitter_idx, cl_uint nparts,
 	CCLBuffer* counts_out, GError** err);
 
+/* Status words of the sorter's last radix call (blocks on the queue): out[0] look-back
+ * timeout flag, out[1] number of tiles whose atomic ranks failed verification and were
+ * redone with the ballot ranks, out[2..17] optional phase profile (CLO_RADIX_PROFILE=1). */
+cl_bool clo_sort_b200_debug(CloSort* sorter, CCLQueue* cq, cl_ulong out[18]);
+
+/* Per-kernel device timing of the sorter's radix calls, taken with CUDA events on the
+ * queue's stream (the analogue of cf4ocl's per-event profiling the reference benches use,
+ * src/benchmarks/clo_sort_bench.c:201-208).  After a call, get_timing returns
+ * out_ms[0] = histogram + bin scan and out_ms[1..] = one value per onesweep pass. */
+void clo_sort_b200_set_timing(CloSort* sorter, cl_bool on);
+cl_uint clo_sort_b200_get_timing(CloSort* sorter, float* out_ms, cl_uint cap);
+
 /* Library / device info. */
 const char* clo_b200_version(void);
 /* number of this library's kernels launched since load (bench evidence) */

@@ -61,14 +61,38 @@ def main():
         b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out, chk, u
         torch.cuda.empty_cache()
 
+    if "sortprof" in what:
+        n = 1 << args.log2n_sort
+        os.environ["CLO_RADIX_PROFILE"] = "1"
+        t_in = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
+        t_out = torch.empty_like(t_in)
+        b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
+        s = clo.CloSort("satradix", ctx, clo.UINT)
+        for _ in range(3):
+            s.with_device_data(q, b_in, b_out, n)
+        d = s.debug(q)
+        print("cfg", os.environ.get("CLO_RADIX_CFG"))
+        names = ["ticket+zero", "load", "rank", "digit phase", "stage", "look-back", "write-out"]
+        tiles = 4 * ((n + 8191) // 8192)
+        tot = sum(d[2:9])
+        print(json.dumps({"sortprof": {"timeout": d[0], "repaired_tiles": d[1], "tiles": tiles,
+                                       "cycles_per_tile": {k: round(v / tiles, 1) for k, v in zip(names, d[2:9])},
+                                       "share": {k: round(v / max(tot, 1), 3) for k, v in zip(names, d[2:9])},
+                                       "walk_cycles": round(d[9] / tiles, 1), "walk_rounds": round(d[10] / tiles, 2),
+                                       "walk_unpublished": round(d[11] / tiles, 2),
+                                       "walk_depth": round(d[12] / tiles, 1)}}), flush=True)
+        os.environ.pop("CLO_RADIX_PROFILE")
+        b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out
+        torch.cuda.empty_cache()
+
     if "sortcfg" in what:
         # tuning sweep of the headline kernel: tile configuration x match method
         n = 1 << args.log2n_sort
         t_in = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
         t_out = torch.empty_like(t_in)
         b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
-        for hw in ("atomic", "ballot"):
-            for cfg in (0, 1, 2, 3, 4):
+        for hw in ("atomic",):
+            for cfg in [int(x) for x in os.environ.get("QB_CFGS", "0,1,2,3,4").split(",")]:
                 os.environ["CLO_RADIX_RANK"] = hw
                 os.environ["CLO_RADIX_CFG"] = str(cfg)
                 s = clo.CloSort("satradix", ctx, clo.UINT)
