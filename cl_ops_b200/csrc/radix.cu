@@ -32,11 +32,12 @@ using namespace clo;
 namespace {
 
 int g_radix_profile = 0;
+int g_pp_flags = 0;
 
 const int RADIX_BITS = 8;
 const int RADIX = 1 << RADIX_BITS;
 const int MAX_PASSES = 8;
-const unsigned SPIN_LIMIT = 1u << 26;
+const unsigned SPIN_LIMIT = 1u << 24;
 const int LB_FIRST = 4;     /* look-back window: first load batch */
 const int LB_NEXT = 4;      /* ... and the following ones */
 
@@ -516,6 +517,8 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	if (full) body(std::true_type{}); else body(std::false_type{});
 }
 
+#include "radix_pp.cuh"
+
 /* ------------------------------------------------------------- host side */
 
 template <typename ElemT, bool HAS_VAL> struct TileCfg {
@@ -537,6 +540,8 @@ struct CloRadixState {
 	CloScratch aux_keys;     /* ping-pong partner of the key buffer */
 	CloScratch aux_vals;
 	CloScratch work;         /* [err | ghist | bins_base | tickets | lookback...] */
+	CloScratch pp;           /* AGG + PREF words of the persistent kernel (self-cleaning) */
+	int kernel_pp = 1;       /* CLO_RADIX_KERNEL=classic selects the one-tile-per-CTA kernel */
 	int rank_atomic = 1;     /* CLO_RADIX_RANK=ballot selects the ballot ranks */
 	int cfg = 0;
 	/* optional per-kernel timing of the last call (clo_radix_set_timing) */
@@ -554,6 +559,10 @@ CloRadixState* clo_radix_state_new() {
 	CloRadixState* st = new CloRadixState();
 	const char* e = getenv("CLO_RADIX_RANK");
 	st->rank_atomic = (e && strcmp(e, "ballot") == 0) ? 0 : 1;
+	const char* kk = getenv("CLO_RADIX_KERNEL");
+	st->kernel_pp = (kk && strcmp(kk, "classic") == 0) ? 0 : 1;
+	const char* ppf = getenv("CLO_RADIX_PP_FLAGS");
+	g_pp_flags = (ppf && *ppf) ? atoi(ppf) : 0;
 	const char* pf = getenv("CLO_RADIX_PROFILE");
 	g_radix_profile = (pf && *pf == '1') ? 1 : 0;
 	const char* c = getenv("CLO_RADIX_CFG");
@@ -577,7 +586,7 @@ int clo_radix_get_timing(CloRadixState* st, float* out, int cap) {
 void clo_radix_state_free(CloRadixState* st) {
 	if (!st) return;
 	for (cudaEvent_t e : st->marks) if (e) cudaEventDestroy(e);
-	st->aux_keys.release(); st->aux_vals.release(); st->work.release();
+	st->aux_keys.release(); st->aux_vals.release(); st->work.release(); st->pp.release();
 	delete st;
 }
 
@@ -649,6 +658,35 @@ cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vo
 	return cudaGetLastError();
 }
 
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int RANK_MODE, int THREADS, int IPT>
+cudaError_t launch_onesweep_pp(const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n,
+		LbT* agg, LbT* pref, u32* ticket, const u64* bins, u32 start_bit, u32 dmask, const CloKeySpec& ks,
+		int* err, int sm_count, cudaStream_t stream) {
+	constexpr size_t SMEM = onesweep_pp_smem<ElemT, HAS_VAL, IDENTITY, THREADS, IPT, LbT>();
+	auto kern = clo_radix_onesweep_pp<ElemT, HAS_VAL, IDENTITY, LbT, THREADS, IPT, RANK_MODE>;
+	static bool configured[64] = {};
+	static int ctas_per_sm[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) dev = 0;
+	if (!configured[dev]) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM);
+		if (e != cudaSuccess) return e;
+		int k = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kern, THREADS, SMEM) != cudaSuccess || k < 1) k = 1;
+		ctas_per_sm[dev] = k;
+		configured[dev] = true;
+	}
+	const size_t tiles = (n + (size_t) THREADS * IPT - 1) / ((size_t) THREADS * IPT);
+	size_t workers = (size_t) sm_count * ctas_per_sm[dev];
+	workers = workers > (size_t) PP_NUM_PROP ? workers - PP_NUM_PROP : 1;
+	if (workers > tiles) workers = tiles;
+	kern<<<(unsigned) (PP_NUM_PROP + workers), THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u32) tiles,
+		agg, pref, ticket, bins, start_bit, dmask, ks, err, g_radix_profile, g_pp_flags);
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
+}
+
 template <typename ElemT, bool IDENTITY, int PASSES, int COLS>
 cudaError_t launch_histogram_p(const ElemT* src, size_t n, u64* ghist, const PassCfg& cfg, const CloKeySpec& ks,
 		int vec_ok, int sm_count, cudaStream_t stream) {
@@ -690,8 +728,17 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 	}
 	const size_t tiles = (n + TILE - 1) / TILE;
 	const bool wide = n >= (1ull << 30);
+	const bool use_pp = st->kernel_pp != 0;
 	WorkLayout L;
-	if ((e = prepare_work(st, tiles, cfg.passes, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
+	if ((e = prepare_work(st, use_pp ? 0 : tiles, cfg.passes, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
+	if (use_pp) {
+		/* AGG + PREF words, shared by all passes; zeroed when (re)allocated, self-cleaning after */
+		const size_t need = 2 * tiles * RADIX * (wide ? 8 : 4);
+		if (need > st->pp.size) {
+			if ((e = st->pp.reserve(need + need / 4)) != cudaSuccess) return e;
+			if ((e = cudaMemsetAsync(st->pp.ptr, 0, st->pp.size, stream)) != cudaSuccess) return e;
+		}
+	}
 	if ((e = st->aux_keys.reserve(n * sizeof(ElemT))) != cudaSuccess) return e;
 	if (HAS_VAL && (e = st->aux_vals.reserve(n * sizeof(u32))) != cudaSuccess) return e;
 	ElemT* aux = (ElemT*) st->aux_keys.ptr;
@@ -726,16 +773,25 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		ElemT* nxt = to_dst ? dst : aux;
 		u32* vnxt = to_dst ? vdst : vaux;
 		u32* ticket = L.tickets + p;
-		if (wide) {
+		if (use_pp) {
+			const u64* bins = L.bins + p * RADIX;
+			if (wide) {
+				u64* agg = (u64*) st->pp.ptr; u64* pref = agg + tiles * RADIX;
+				e = st->rank_atomic
+					? launch_onesweep_pp<ElemT, HAS_VAL, IDENTITY, u64, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, agg, pref, ticket, bins, cfg.start_bit[p], cfg.dmask[p], ks, L.err, sm_count, stream)
+					: launch_onesweep_pp<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, agg, pref, ticket, bins, cfg.start_bit[p], cfg.dmask[p], ks, L.err, sm_count, stream);
+			} else {
+				u32* agg = (u32*) st->pp.ptr; u32* pref = agg + tiles * RADIX;
+				e = st->rank_atomic
+					? launch_onesweep_pp<ElemT, HAS_VAL, IDENTITY, u32, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, agg, pref, ticket, bins, cfg.start_bit[p], cfg.dmask[p], ks, L.err, sm_count, stream)
+					: launch_onesweep_pp<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, agg, pref, ticket, bins, cfg.start_bit[p], cfg.dmask[p], ks, L.err, sm_count, stream);
+			}
+		} else if (wide) {
 			u64* lb = (u64*) L.lookback + (size_t) p * tiles * RADIX;
-			e = st->rank_atomic
-				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 1, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
-				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+			e = launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		} else {
 			u32* lb = (u32*) L.lookback + (size_t) p * tiles * RADIX;
-			e = st->rank_atomic
-				? launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 1, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream)
-				: launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
+			e = launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		}
 		if (e != cudaSuccess) return e;
 		st->mark(stream);
@@ -749,24 +805,6 @@ cudaError_t radix_sort_typed(CloRadixState* st, int sm_count, const CloKeySpec& 
 		const ElemT* src, ElemT* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
 	return radix_sort_cfg<ElemT, HAS_VAL, IDENTITY, TileCfg<ElemT, HAS_VAL>::THREADS, TileCfg<ElemT, HAS_VAL>::IPT>(
 		st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-}
-
-/* tuning variants for the headline case (u32 keys only, identity key), chosen with
- * CLO_RADIX_CFG; the default is TileCfg */
-template <>
-cudaError_t radix_sort_typed<u32, false, true>(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
-		const u32* src, u32* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
-	switch (st->cfg) {
-	case 1: return radix_sort_cfg<u32, false, true, 256, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 2: return radix_sort_cfg<u32, false, true, 384, 18>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 3: return radix_sort_cfg<u32, false, true, 256, 12>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 4: return radix_sort_cfg<u32, false, true, 512, 12>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 5: return radix_sort_cfg<u32, false, true, 512, 16, 16, 32>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 6: return radix_sort_cfg<u32, false, true, 512, 16, 32, 32>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 7: return radix_sort_cfg<u32, false, true, 512, 16, 48, 32>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	case 8: return radix_sort_cfg<u32, false, true, 512, 16, 4, 4>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	default: return radix_sort_cfg<u32, false, true, 512, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	}
 }
 
 template <typename ElemT>

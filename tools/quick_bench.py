@@ -72,7 +72,9 @@ def main():
             s.with_device_data(q, b_in, b_out, n)
         d = s.debug(q)
         print("cfg", os.environ.get("CLO_RADIX_CFG"))
-        names = ["ticket+zero", "load", "rank", "digit phase", "stage", "look-back", "write-out"]
+        names = ["zero+loadwait", "rank", "digit phase", "stage", "ticket+loadissue", "prefix wait", "write-out"]
+        if os.environ.get("CLO_RADIX_KERNEL") == "classic":
+            names = ["ticket+zero", "load", "rank", "digit phase", "stage", "look-back", "write-out"]
         tiles = 4 * ((n + 8191) // 8192)
         tot = sum(d[2:9])
         print(json.dumps({"sortprof": {"timeout": d[0], "repaired_tiles": d[1], "tiles": tiles,
@@ -80,7 +82,8 @@ def main():
                                        "share": {k: round(v / max(tot, 1), 3) for k, v in zip(names, d[2:9])},
                                        "walk_cycles": round(d[9] / tiles, 1), "walk_rounds": round(d[10] / tiles, 2),
                                        "walk_unpublished": round(d[11] / tiles, 2),
-                                       "walk_depth": round(d[12] / tiles, 1)}}), flush=True)
+                                       "walk_depth": round(d[12] / tiles, 1),
+                                       "prop_cycles_total": d[14], "prop_empty_polls": d[15]}}), flush=True)
         os.environ.pop("CLO_RADIX_PROFILE")
         b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out
         torch.cuda.empty_cache()
