@@ -807,6 +807,15 @@ cudaError_t radix_sort_typed(CloRadixState* st, int sm_count, const CloKeySpec& 
 		st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 }
 
+/* tile-shape variant of the headline case (u32 keys only, identity key): CLO_RADIX_CFG=1 */
+template <>
+cudaError_t radix_sort_typed<u32, false, true>(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
+		const u32* src, u32* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
+	if (st->cfg == 1)
+		return radix_sort_cfg<u32, false, true, 256, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	return radix_sort_cfg<u32, false, true, 512, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+}
+
 template <typename ElemT>
 cudaError_t radix_sort_elem(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
 		const void* src, void* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {

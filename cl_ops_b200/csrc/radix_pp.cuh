@@ -25,7 +25,7 @@
 #define CLO_RADIX_PP_CUH
 
 const int PP_NUM_PROP = 8;    /* propagator CTAs: RADIX / 32 digits each */
-const int PP_U = 8;           /* tiles per warp per propagator iteration (window = 16 warps x 8 = 128 tiles) */
+const int PP_WINDOW = 128;    /* tiles a propagator looks at per iteration */
 
 template <typename LbT> struct PPWord;
 template <> struct PPWord<u32> { static constexpr u32 VALID = 1u << 31, VAL = (1u << 31) - 1; };
@@ -40,7 +40,8 @@ template <typename LbT, int THREADS>
 __device__ __forceinline__ void pp_propagate(LbT* __restrict__ agg, LbT* __restrict__ pref, u32 num_tiles,
 		int* __restrict__ err_flag, unsigned char* smem_raw, int prof_on) {
 	constexpr int WARPS = THREADS / 32;
-	constexpr int R = WARPS * PP_U;                /* window: tiles per iteration */
+	constexpr int PP_U = PP_WINDOW / WARPS;        /* window entries per thread */
+	constexpr int R = PP_WINDOW;                   /* window: tiles per iteration */
 	constexpr int SEG = 4;                         /* warps doing the serial part */
 	static_assert(R % SEG == 0, "window must split into segments");
 	LbT* s_val = reinterpret_cast<LbT*>(smem_raw);         /* [R][32] */
@@ -58,14 +59,17 @@ __device__ __forceinline__ void pp_propagate(LbT* __restrict__ agg, LbT* __restr
 	__syncthreads();
 	u32 t0 = 0;
 	int par = 0;
-	while (t0 < num_tiles) {
-		/* window entry j = u * WARPS + warp is tile t0 + j */
-		LbT w[PP_U];
+	/* window entry j = u * WARPS + warp is tile t0 + j */
+	LbT w[PP_U];
+	auto load_window = [&](u32 base) {
 #pragma unroll
 		for (int u = 0; u < PP_U; ++u) {
-			const u32 t = t0 + u * WARPS + warp;
+			const u32 t = base + u * WARPS + warp;
 			w[u] = (t < num_tiles) ? ld_relaxed(agg + (size_t) t * RADIX + d) : (LbT) 0;
 		}
+	};
+	load_window(0);
+	while (t0 < num_tiles) {
 		int first_bad = R;
 #pragma unroll
 		for (int u = PP_U - 1; u >= 0; --u) {
@@ -83,6 +87,10 @@ __device__ __forceinline__ void pp_propagate(LbT* __restrict__ agg, LbT* __restr
 		__syncthreads();
 		const int L = s_first[par];                /* tiles t0 .. t0+L-1 are complete */
 		if (threadIdx.x == 0) s_first[par ^ 1] = R;   /* reset the other slot for the next iteration */
+		/* The next window starts at t0 + L.  Its loads are issued NOW, before this
+		 * iteration's scan and stores, so that one L2 round trip overlaps the other work (and
+		 * is not ordered behind the strong stores below).  s_val already holds this window. */
+		load_window(t0 + (u32) L);
 		if (L == 0) {
 			if (++idle > (SPIN_LIMIT >> 3)) { atomicExch(err_flag, 1); break; }
 			par ^= 1;
@@ -145,7 +153,7 @@ __device__ __forceinline__ void pp_propagate(LbT* __restrict__ agg, LbT* __restr
 }
 
 template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int THREADS, int IPT, int RANK_MODE>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, (THREADS >= 512 ? 2 : 4))
 clo_radix_onesweep_pp(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n, u32 num_tiles,
 		LbT* __restrict__ agg, LbT* __restrict__ pref, u32* __restrict__ ticket,
@@ -468,7 +476,7 @@ constexpr size_t onesweep_pp_smem() {
 	constexpr size_t worker = (size_t) (THREADS / 32) * RADIX * 4 + 2 * RADIX * 4 + 4 * RADIX * 4 + 16 * 4 +
 		2 * ((size_t) THREADS * IPT * sizeof(ElemT) + (USE_INFO ? (size_t) THREADS * IPT * 4 : 0) +
 			(HAS_VAL ? (size_t) THREADS * IPT * 4 : 0));
-	constexpr size_t prop = ((size_t) (THREADS / 32) * PP_U * 32 + 8 * 32) * sizeof(LbT) + 16;
+	constexpr size_t prop = ((size_t) PP_WINDOW * 32 + 8 * 32) * sizeof(LbT) + 16;
 	return worker > prop ? worker : prop;
 }
 
