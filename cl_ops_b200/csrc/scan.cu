@@ -264,6 +264,8 @@ __global__ void clo_scan_reduce_final(const typename AccOf<SumT>::type* __restri
 	}
 }
 
+#include "scan_pp.cuh"
+
 /* --------------------------------------------------------------- host side */
 
 struct ScanState {
@@ -272,6 +274,10 @@ struct ScanState {
 	u32 epoch = 0;
 	int cfg = 0;               /* CLO_SCAN_CFG: tile shape variants of the u32->u32 kernel */
 	CloScratch partials;
+	CloScratch pp;             /* persistent kernel: [ticket | pad][AGG words][PREF words] */
+	size_t pp_tiles_cap = 0;
+	u32 pp_epoch = 0;
+	int use_pp = 1;            /* CLO_SCAN_KERNEL=classic selects the one-tile-per-CTA kernel */
 };
 
 const size_t HDR_BYTES = 256;
@@ -318,11 +324,87 @@ cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, cons
 	return launch_scan_cfg<ElemT, SumT, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream);
 }
 
+/* persistent kernel (scan_pp.cuh): used for large, 16-byte aligned inputs of the hot type pairs */
+const size_t SPP_MIN_ELEMS = (size_t) 1 << 22;
+
+template <typename ElemT, typename SumT, int THREADS = SPP_THREADS, int VPT = SPP_VPT, int AHEAD = SPP_AHEAD, int LAG = SPP_LAG>
+cudaError_t launch_scan_pp(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) {
+	typedef typename AccOf<SumT>::type AccT;
+	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
+	constexpr size_t TILE = (size_t) THREADS * VPT * EPV;
+	constexpr size_t SMEM = (size_t) (AHEAD + 1 + LAG) * TILE * sizeof(ElemT);
+	const size_t tiles = (n + TILE - 1) / TILE;
+	cudaError_t e;
+	if (tiles > st.pp_tiles_cap) {
+		size_t cap = tiles + tiles / 4 + 1024;
+		if ((e = st.pp.reserve(HDR_BYTES + cap * 4 * sizeof(u64))) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(st.pp.ptr, 0, st.pp.size, stream)) != cudaSuccess) return e;
+		st.pp_tiles_cap = cap; st.pp_epoch = 0;
+	}
+	if (st.pp_epoch >= 0xfffffff0u) {
+		if ((e = cudaMemsetAsync(st.pp.ptr, 0, st.pp.size, stream)) != cudaSuccess) return e;
+		st.pp_epoch = 0;
+	}
+	st.pp_epoch += 1;
+	u32* ticket = (u32*) st.pp.ptr;
+	int* err_flag = (int*) st.pp.ptr + 1;
+	u64* agg = (u64*) ((char*) st.pp.ptr + HDR_BYTES);
+	u64* pref = agg + st.pp_tiles_cap * 2;
+	if ((e = cudaMemsetAsync(ticket, 0, sizeof(u32), stream)) != cudaSuccess) return e;
+	auto kern = clo_scan_pp<ElemT, SumT, THREADS, VPT, AHEAD, LAG>;
+	static int ctas_per_sm = 0;
+	if (!ctas_per_sm) {
+		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
+		int k = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kern, THREADS, SMEM) != cudaSuccess || k < 1) k = 1;
+		ctas_per_sm = k;
+	}
+	size_t workers = (size_t) sms * ctas_per_sm - 1;
+	if (workers > tiles) workers = tiles;
+	kern<<<(unsigned) (1 + workers), THREADS, SMEM, stream>>>((const ElemT*) in, (SumT*) out, n, (u32) tiles,
+		agg, pref, ticket, st.pp_epoch, (const SumT*) carry, err_flag);
+	CLO_COUNT_LAUNCH(1);
+	(void) sizeof(AccT);
+	return cudaGetLastError();
+}
+
+template <typename ElemT, typename SumT>
+bool scan_pp_applicable(const ScanState& st, const void* in, const void* out, size_t n) {
+	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
+	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
+	return st.use_pp && n >= SPP_MIN_ELEMS && (reinterpret_cast<uintptr_t>(in) % 16) == 0 &&
+		(reinterpret_cast<uintptr_t>(out) % (sizeof(SumT) * OCH)) == 0;
+}
+
+#define CLO_SCAN_PP_PAIR(E, S) \
+template <> \
+cudaError_t launch_scan<E, S>(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) { \
+	if (scan_pp_applicable<E, S>(st, in, out, n)) return launch_scan_pp<E, S>(st, in, out, n, carry, sms, stream); \
+	return launch_scan_cfg<E, S, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream); \
+}
+CLO_SCAN_PP_PAIR(unsigned int, unsigned long long)
+CLO_SCAN_PP_PAIR(int, int)
+CLO_SCAN_PP_PAIR(int, long long)
+CLO_SCAN_PP_PAIR(float, float)
+CLO_SCAN_PP_PAIR(float, double)
+CLO_SCAN_PP_PAIR(unsigned long long, unsigned long long)
+CLO_SCAN_PP_PAIR(double, double)
+#undef CLO_SCAN_PP_PAIR
+
 /* tuning variants of the headline type pair */
 template <>
 cudaError_t launch_scan<unsigned int, unsigned int>(ScanState& st, const void* in, void* out, size_t n,
 		const void* carry, int sms, cudaStream_t stream) {
-	(void) sms;
+	if (scan_pp_applicable<unsigned int, unsigned int>(st, in, out, n)) {
+		switch (st.cfg) {      /* CLO_SCAN_CFG 10..: shapes of the persistent kernel */
+		case 11: return launch_scan_pp<unsigned int, unsigned int, 512, 2, 1, 4>(st, in, out, n, carry, sms, stream);
+		case 12: return launch_scan_pp<unsigned int, unsigned int, 256, 2, 1, 8>(st, in, out, n, carry, sms, stream);
+		case 13: return launch_scan_pp<unsigned int, unsigned int, 128, 4, 1, 6>(st, in, out, n, carry, sms, stream);
+		case 14: return launch_scan_pp<unsigned int, unsigned int, 256, 3, 1, 6>(st, in, out, n, carry, sms, stream);
+		case 15: return launch_scan_pp<unsigned int, unsigned int, 512, 4, 1, 1>(st, in, out, n, carry, sms, stream);
+		default: return launch_scan_pp<unsigned int, unsigned int>(st, in, out, n, carry, sms, stream);
+		}
+	}
 	switch (st.cfg) {
 	case 1: return launch_scan_cfg<unsigned int, unsigned int, 256, 4, 5>(st, in, out, n, carry, stream);
 	case 2: return launch_scan_cfg<unsigned int, unsigned int, 128, 8, 6>(st, in, out, n, carry, stream);
@@ -439,11 +521,14 @@ static const char* blelloch_init(CloScan* scanner, const char* options, GError**
 static void blelloch_finalize(CloScan* scanner) { (void) scanner; }
 
 static int scan_check_error_flag(CloScan* scanner, cudaStream_t stream, GError** err) {
-	if (!scanner->st.scratch.ptr) return 0;
-	int flag = 0;
-	if (clo_cuda_failed(cudaMemcpyAsync(&flag, (int*) scanner->st.scratch.ptr + 1, sizeof(int),
+	if (!scanner->st.scratch.ptr && !scanner->st.pp.ptr) return 0;
+	int flag = 0, flag2 = 0;
+	if (scanner->st.scratch.ptr && clo_cuda_failed(cudaMemcpyAsync(&flag, (int*) scanner->st.scratch.ptr + 1, sizeof(int),
+			cudaMemcpyDeviceToHost, stream), err, "scan status read")) return 1;
+	if (scanner->st.pp.ptr && clo_cuda_failed(cudaMemcpyAsync(&flag2, (int*) scanner->st.pp.ptr + 1, sizeof(int),
 			cudaMemcpyDeviceToHost, stream), err, "scan status read")) return 1;
 	if (clo_cuda_failed(cudaStreamSynchronize(stream), err, "scan sync")) return 1;
+	flag |= flag2;
 	if (flag) {
 		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "scan look-back timed out (device status flag set)");
 		return 1;
@@ -526,6 +611,7 @@ extern "C" CloScan* clo_scan_new(const char* type, const char* options, CCLConte
 	s->data = NULL;
 	s->fn = fn; s->rfn = find_reduce((int) elem_type, (int) sum_type);
 	{ const char* c = getenv("CLO_SCAN_CFG"); s->st.cfg = (c && *c) ? atoi(c) : 0; }
+	{ const char* c = getenv("CLO_SCAN_KERNEL"); s->st.use_pp = (c && strcmp(c, "classic") == 0) ? 0 : 1; }
 	GError* ierr = NULL;
 	s->impl_def.init(s, options, &ierr);
 	if (ierr) { g_propagate_error(err, ierr); clo_scan_destroy(s); return NULL; }
@@ -541,6 +627,7 @@ extern "C" void clo_scan_destroy(CloScan* scan) {
 		CloDeviceGuard g(scan->ctx->dev.ordinal);
 		scan->st.scratch.release();
 		scan->st.partials.release();
+		scan->st.pp.release();
 	}
 	ccl_context_unref(scan->ctx);
 	delete scan;

@@ -10,7 +10,7 @@ import oracle
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [1, 2, 3, 31, 257, 4096, 4097, 12289, 100003, (1 << 20) + 3]
+SIZES = [1, 2, 3, 31, 257, 4096, 4097, 12289, 100003, (1 << 20) + 3, (1 << 22) + 5]
 INT_PAIRS = [(oracle.UINT, oracle.UINT), (oracle.UINT, oracle.ULONG), (oracle.INT, oracle.LONG),
              (oracle.UCHAR, oracle.UINT), (oracle.USHORT, oracle.ULONG), (oracle.ULONG, oracle.ULONG),
              (oracle.CHAR, oracle.INT), (oracle.LONG, oracle.UINT), (oracle.SHORT, oracle.USHORT),
@@ -94,6 +94,32 @@ def test_scan_device_data_carry_and_reduce(clo, ctx, queue):
     queue.finish()
     assert np.array_equal(t_out.cpu().numpy().view(np.uint64), oracle.scan(a, oracle.UINT, oracle.ULONG))
     for b in (b_in, b_out, b_carry, b_total):
+        b.destroy()
+    s.destroy()
+
+
+@pytest.mark.parametrize("kernel", ["pp", "classic"])
+def test_scan_large_both_kernels(clo, ctx, queue, kernel, monkeypatch):
+    """the persistent (propagator) kernel and the one-tile-per-CTA kernel give the same bits;
+    carry-in goes through the propagator in the persistent kernel"""
+    import torch
+    monkeypatch.setenv("CLO_SCAN_KERNEL", kernel)
+    n = (1 << 24) + 4099
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    t_in = torch.from_numpy(a.view(np.int32)).cuda()
+    t_out = torch.empty(n, dtype=torch.int64, device="cuda")
+    t_carry = torch.tensor([2**40 + 7], dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    b_in, b_out, b_c = (clo.Buffer.wrap_tensor(ctx, t) for t in (t_in, t_out, t_carry))
+    s = clo.CloScan("blelloch", ctx, oracle.UINT, oracle.ULONG)
+    want = oracle.scan(a, oracle.UINT, oracle.ULONG)
+    for rep in range(3):      # repeated calls exercise the epoch tags
+        s.with_device_data(queue, b_in, b_out, n, carry_in=b_c if rep == 1 else None)
+        queue.finish()
+        w = want + np.uint64(2**40 + 7) if rep == 1 else want
+        assert np.array_equal(t_out.cpu().numpy().view(np.uint64), w), "rep %d" % rep
+    for b in (b_in, b_out, b_c):
         b.destroy()
     s.destroy()
 

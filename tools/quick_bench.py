@@ -183,7 +183,7 @@ def main():
         t_in = torch.randint(0, 128, (n,), dtype=torch.int32, device="cuda")
         t_out = torch.empty_like(t_in)
         b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
-        for cfg in range(6):
+        for cfg in [int(x) for x in os.environ.get("QB_SCAN_CFGS", "0,1,2,3,4,5").split(",")]:
             os.environ["CLO_SCAN_CFG"] = str(cfg)
             s = clo.CloScan("blelloch", ctx, clo.UINT, clo.UINT)
             med, best = timed(lambda: s.with_device_data(q, b_in, b_out, n), args.iters)
