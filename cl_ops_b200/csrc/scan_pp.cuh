@@ -154,6 +154,9 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 		const SumT* __restrict__ carry_in, int* __restrict__ err_flag) {
 	typedef typename AccOf<SumT>::type AccT;
 	typedef AccWords<AccT> AW;
+	/* tile-local arithmetic: f32 for f32 sums (a 4096-element shuffle/tree sum loses ~1e-6
+	 * relative, far inside the stated tolerance); everything between tiles stays in AccT (f64) */
+	typedef typename std::conditional<std::is_same<SumT, float>::value, float, AccT>::type IntraT;
 	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;          /* elements per vector */
 	constexpr int VB = EPV * (int) sizeof(ElemT);             /* vector bytes: 4, 8 or 16 */
 	static_assert(VB == 16, "the ring is filled with 16-byte cp.async");
@@ -225,16 +228,16 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 		if (r >= 0 && t_red < num_tiles) {
 			spp_cp_async_wait<AHEAD_>();
 			const ElemT* src = ring + (size_t) (r % S) * TILE;
-			AccT sum = AccT(0);
+			IntraT sum = IntraT(0);
 #pragma unroll
 			for (int j = 0; j < VPT; ++j) {
 				ElemT e[EPV];
 				*reinterpret_cast<uint4*>(e) = *reinterpret_cast<const uint4*>(src + lane_off + (u32) j * 32 * EPV);
 #pragma unroll
-				for (int c = 0; c < EPV; ++c) sum += to_acc<ElemT, SumT, AccT>(e[c]);
+				for (int c = 0; c < EPV; ++c) sum += to_acc<ElemT, SumT, IntraT>(e[c]);
 			}
-			sum = warp_reduce_sum<AccT>(sum);
-			if (lane == 0) s_wsum[r % S][warp] = sum;
+			sum = warp_reduce_sum<IntraT>(sum);
+			if (lane == 0) s_wsum[r % S][warp] = static_cast<AccT>(sum);
 		}
 		__syncthreads();
 		if (r >= 0 && t_red < num_tiles && tid == 0) {
@@ -267,21 +270,29 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 				const u32 o = lane_off + (u32) j * 32 * EPV;
 				ElemT e[EPV];
 				*reinterpret_cast<uint4*>(e) = *reinterpret_cast<const uint4*>(src + o);
-				AccT v[EPV];
+				IntraT v[EPV];
 #pragma unroll
-				for (int c = 0; c < EPV; ++c) v[c] = to_acc<ElemT, SumT, AccT>(e[c]);
+				for (int c = 0; c < EPV; ++c) v[c] = to_acc<ElemT, SumT, IntraT>(e[c]);
 #pragma unroll
 				for (int c = 1; c < EPV; ++c) v[c] += v[c - 1];
-				const AccT incl = warp_inclusive_scan<AccT>(v[EPV - 1], lane);
-				AccT excl = __shfl_up_sync(0xffffffffu, incl, 1);
-				if (lane == 0) excl = AccT(0);
-				const AccT row_total = __shfl_sync(0xffffffffu, incl, 31);
-				const AccT b = row_off + excl;
-				row_off += row_total;
+				const IntraT incl = warp_inclusive_scan<IntraT>(v[EPV - 1], lane);
+				IntraT excl = __shfl_up_sync(0xffffffffu, incl, 1);
+				if (lane == 0) excl = IntraT(0);
+				const IntraT row_total = __shfl_sync(0xffffffffu, incl, 31);
+				const AccT b = row_off + static_cast<AccT>(excl);
+				row_off += static_cast<AccT>(row_total);
 				SumT ov[EPV];
-				ov[0] = static_cast<SumT>(b);
+				if (std::is_same<SumT, float>::value) {
+					/* round the f64 base once per vector; one more f32 rounding per element */
+					const IntraT bf = static_cast<IntraT>(b);
+					ov[0] = static_cast<SumT>(bf);
 #pragma unroll
-				for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(b + v[c - 1]);
+					for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(bf + v[c - 1]);
+				} else {
+					ov[0] = static_cast<SumT>(b);
+#pragma unroll
+					for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(b + static_cast<AccT>(v[c - 1]));
+				}
 				const size_t idx = base + o;
 				if (full || idx + EPV <= n) {
 #pragma unroll
