@@ -217,7 +217,8 @@ def run_ours(args):
         del u
         dbg = sorter.debug(queue)
     else:
-        k_sorted, _, info = step()
+        k_sorted, _, info = cdist.sample_sort(t_in, None, ops, 32, profile=True)
+        phases = info.get("phases_ms", {})
         u = k_sorted.to(torch.int64) & 0xFFFFFFFF
         ok = bool((u[1:] >= u[:-1]).all().item()) if u.numel() > 1 else True
         edges = torch.zeros(2 * world, dtype=torch.int64, device="cuda")
@@ -298,6 +299,9 @@ def run_ours(args):
             "repaired_tiles": int(dbg[1]), "lookback_timeout": int(dbg[0]),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         }
+        if distributed:
+            out["phases_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
+            out["exchange"] = {"sent_keys_rank0": info["sent"], "received_keys_rank0": info["received"]}
         print(json.dumps(out))
     b_in.destroy(); b_out.destroy(); sorter.destroy()
     if ops:

@@ -92,7 +92,27 @@ def choose_splitters(sample_keys_i64, sample_idx, nparts):
     return sel
 
 
-def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None):
+class _Phases:
+    """optional per-phase device timing (CUDA events) for profiling the sample sort"""
+
+    def __init__(self, enabled):
+        self.enabled, self.marks = enabled, []
+
+    def mark(self, name):
+        if self.enabled:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def result(self):
+        if not self.enabled or len(self.marks) < 2:
+            return {}
+        torch.cuda.synchronize()
+        return {self.marks[i + 1][0]: self.marks[i][1].elapsed_time(self.marks[i + 1][1])
+                for i in range(len(self.marks) - 1)}
+
+
+def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None, profile=False):
     """Globally stable sort of the concatenation of every rank's `keys` (rank order).
 
     keys: 1-D int32 (u32 bit pattern) or int64 (u64 bit pattern) tensor on this rank.
@@ -104,6 +124,8 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None)
     r = dist.get_rank(group)
     dev = keys.device
     n_local = keys.numel()
+    ph = _Phases(profile and keys.is_cuda)
+    ph.mark("start")
 
     # global index of my first element (ranks may hold different counts)
     n_all = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -134,6 +156,7 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None)
     valid = all_i >= 0
     all_k, all_i = all_k[valid], all_i[valid]
 
+    ph.mark("samples+allgather")
     # 2) splitters (identical on every rank: same data, same deterministic procedure)
     sel = choose_splitters(all_k, all_i, P)
     spl_k64, spl_i = all_k[sel], all_i[sel]
@@ -143,8 +166,10 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None)
         spl_keys = spl_k64 ^ _SIGN64
     spl_keys, spl_i = spl_keys.contiguous(), spl_i.contiguous()
 
+    ph.mark("splitters")
     # 3) stable local partition into P buckets; bucket sizes
     part_k, part_p, counts = ops.partition(keys, payload, gidx0, spl_keys, spl_i, P)
+    ph.mark("partition")
 
     # 4) exchange: counts, then the buckets (all-to-all-v)
     recv_counts = torch.empty_like(counts)
@@ -161,11 +186,13 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None)
         dist.all_to_all_single(recv_p, part_p, output_split_sizes=recv_list, input_split_sizes=send_list,
                                group=group)
 
+    ph.mark("exchange")
     # 5) stable local sort of what arrived (chunks are in source-rank order, each in its
     #    original order, so a stable sort keeps the global order of equal keys)
     out_k, out_p = ops.sort(recv_k, recv_p)
+    ph.mark("local sort")
     info = {"sent": n_local - send_list[r], "received": n_recv, "gidx0": gidx0,
-            "send_counts": send_list, "recv_counts": recv_list}
+            "send_counts": send_list, "recv_counts": recv_list, "phases_ms": ph.result()}
     return out_k, out_p, info
 
 
