@@ -34,10 +34,8 @@ namespace {
 int g_radix_profile = 0;
 int g_pp_flags = 0;
 
-const int RADIX_BITS = 8;
-const int RADIX = 1 << RADIX_BITS;
+#include "radix_prop.cuh"
 const int MAX_PASSES = 8;
-const unsigned SPIN_LIMIT = 1u << 24;
 const int LB_FIRST = 4;     /* look-back window: first load batch */
 const int LB_NEXT = 4;      /* ... and the following ones */
 
@@ -156,25 +154,6 @@ clo_radix_scan_bins(const u64* __restrict__ ghist, u64* __restrict__ bins_base) 
 }
 
 /* -------------------------------------------------------------- onesweep */
-
-/* lanes of the warp whose digit equals mine: one ballot per digit bit, 4 SASS
- * instructions per bit (test, vote, conditional invert, and) */
-__device__ __forceinline__ u32 match_digit_ballot(u32 d) {
-	u32 peers = 0xffffffffu;
-#pragma unroll
-	for (int b = 0; b < RADIX_BITS; ++b) {
-		asm("{\n\t"
-			".reg .pred p;\n\t"
-			".reg .b32 m, t;\n\t"
-			"and.b32 t, %1, %2;\n\t"
-			"setp.ne.u32 p, t, 0;\n\t"
-			"vote.sync.ballot.b32 m, p, 0xffffffff;\n\t"
-			"@!p not.b32 m, m;\n\t"
-			"and.b32 %0, %0, m;\n\t"
-			"}" : "+r"(peers) : "r"(d), "r"(1u << b));
-	}
-	return peers;
-}
 
 /* A digit functor for the sample-sort partition: bucket = number of splitters
  * (key, global index) that are <= (my key, my global index). */
@@ -542,6 +521,7 @@ struct CloRadixState {
 	CloScratch work;         /* [err | ghist | bins_base | tickets | lookback...] */
 	CloScratch pp;           /* AGG + PREF words of the persistent kernel (self-cleaning) */
 	int kernel_pp = 1;       /* CLO_RADIX_KERNEL=classic selects the one-tile-per-CTA kernel */
+	int kernel_v6 = 1;       /* keys-only sorts use the two-barrier kernel; CLO_RADIX_KERNEL=pp|classic turn it off */
 	int rank_atomic = 1;     /* CLO_RADIX_RANK=ballot selects the ballot ranks */
 	int cfg = 0;
 	/* optional per-kernel timing of the last call (clo_radix_set_timing) */
@@ -561,6 +541,7 @@ CloRadixState* clo_radix_state_new() {
 	st->rank_atomic = (e && strcmp(e, "ballot") == 0) ? 0 : 1;
 	const char* kk = getenv("CLO_RADIX_KERNEL");
 	st->kernel_pp = (kk && strcmp(kk, "classic") == 0) ? 0 : 1;
+	st->kernel_v6 = (kk && (strcmp(kk, "classic") == 0 || strcmp(kk, "pp") == 0)) ? 0 : 1;
 	const char* ppf = getenv("CLO_RADIX_PP_FLAGS");
 	g_pp_flags = (ppf && *ppf) ? atoi(ppf) : 0;
 	const char* pf = getenv("CLO_RADIX_PROFILE");
@@ -773,7 +754,18 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		ElemT* nxt = to_dst ? dst : aux;
 		u32* vnxt = to_dst ? vdst : vaux;
 		u32* ticket = L.tickets + p;
-		if (use_pp) {
+		bool done_v6 = false;
+		if constexpr (!HAS_VAL && IDENTITY && sizeof(ElemT) >= 4 && THREADS >= 2 * RADIX) {
+			if (use_pp && st->kernel_v6) {
+				char* agg = (char*) st->pp.ptr;
+				char* pref = agg + tiles * RADIX * (wide ? 8 : 4);
+				e = clo_radix_v6_pass((int) sizeof(ElemT), wide ? 1 : 0, THREADS * IPT, cur, nxt, n, agg, pref, ticket,
+					L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], L.err, sm_count, g_radix_profile, g_pp_flags, stream);
+				done_v6 = true;
+			}
+		}
+		if (done_v6) {
+		} else if (use_pp) {
 			const u64* bins = L.bins + p * RADIX;
 			if (wide) {
 				u64* agg = (u64*) st->pp.ptr; u64* pref = agg + tiles * RADIX;

@@ -94,8 +94,14 @@ template <> struct Gen<R_PARKMILLER> {
 	typedef int State;
 	__device__ static State from_seed(u64 s) { return (int) (u32) s; }
 	__device__ static u32 next(State& s) {
-		long long p = (long long) s * 16807ll;
-		s = (int) (p % 2147483647ll);
+		/* |s| * 16807 < 2^46; 2^31 = 1 (mod 2^31-1), so two folds of the high bits replace the
+		 * 64-bit division; the truncating remainder takes the sign of the dividend */
+		const u32 a = s < 0 ? 0u - (u32) s : (u32) s;
+		const u32 lo = a * 16807u, hi = __umulhi(a, 16807u);
+		u32 r = (lo & 0x7fffffffu) + ((hi << 1) | (lo >> 31));
+		r = (r & 0x7fffffffu) + (r >> 31);
+		if (r >= 0x7fffffffu) r -= 0x7fffffffu;
+		s = s < 0 ? -(int) r : (int) r;
 		return ((u32) s) << 1;
 	}
 };

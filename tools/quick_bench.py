@@ -73,6 +73,8 @@ def main():
         d = s.debug(q)
         print("cfg", os.environ.get("CLO_RADIX_CFG"))
         names = ["zero+loadwait", "rank", "digit phase", "stage", "ticket+loadissue", "prefix wait", "write-out"]
+        if os.environ.get("CLO_RADIX_KERNEL") is None:
+            names = ["P1 count+loadwait", "B1 wait", "P2 digits", "B2 wait", "P3 place", "P4 load issue", "P5 write-out"]
         if os.environ.get("CLO_RADIX_KERNEL") == "classic":
             names = ["ticket+zero", "load", "rank", "digit phase", "stage", "look-back", "write-out"]
         tiles = 4 * ((n + 8191) // 8192)
