@@ -157,4 +157,112 @@ __device__ __forceinline__ void pp_propagate(LbT* __restrict__ agg, LbT* __restr
 	}
 }
 
+
+/* Second-generation propagator: G independent groups per CTA (one named barrier each), each
+ * group owns 32 digits (lane = digit) and looks at a window of PP2_WINDOW tiles per round;
+ * warp wg of the group owns a CONTIGUOUS chunk of C = window / warps-per-group tiles, scans it
+ * in registers and publishes only its chunk total -- no window-wide shared-memory scan, one
+ * barrier per round.  Same protocol and invariant as pp_propagate:
+ * at the top of a round AGG of tiles < t0 is consumed (reset), PREF of tiles <= t0 published. */
+const int PP2_WINDOW = 128;
+
+template <typename LbT, int THREADS, int G>
+__device__ __forceinline__ void pp_propagate2(LbT* __restrict__ agg, LbT* __restrict__ pref, u32 num_tiles,
+		int* __restrict__ err_flag, unsigned char* smem_raw, int prof_on, int cta_index) {
+	constexpr int WARPS = THREADS / 32;
+	constexpr int WPG = WARPS / G;                 /* warps per group */
+	constexpr int C = PP2_WINDOW / WPG;            /* tiles per warp and round */
+	static_assert(WARPS % G == 0 && PP2_WINDOW % WPG == 0, "bad propagator shape");
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int grp = warp / WPG, wg = warp % WPG;
+	/* shared: per group, double buffered: fb[WPG] ints + tot[WPG][32] LbT */
+	LbT* s_tot = reinterpret_cast<LbT*>(smem_raw) + (size_t) grp * 2 * WPG * 32;          /* [2][WPG][32] */
+	int* s_fb = reinterpret_cast<int*>(reinterpret_cast<LbT*>(smem_raw) + (size_t) G * 2 * WPG * 32) + grp * 2 * WPG;   /* [2][WPG] */
+	const u32 d = (u32) (cta_index * G + grp) * 32u + lane;
+	const int bar_id = 1 + grp;
+	LbT running = 0;
+	unsigned idle = 0;
+	u64* prof = reinterpret_cast<u64*>(err_flag + 16);
+	const long long p_t0 = prof_on ? clock64() : 0;
+	unsigned long long rounds = 0;
+	if (wg == 0) st_relaxed(pref + d, (LbT) PPWord<LbT>::VALID);      /* PREF[0] = 0 */
+	u32 t0 = 0;
+	int par = 0;
+	LbT w[C];
+	auto load_window = [&](u32 base) {
+#pragma unroll
+		for (int u = 0; u < C; ++u) {
+			const u32 t = base + (u32) (wg * C + u);
+			w[u] = (t < num_tiles) ? ld_relaxed(agg + (size_t) t * RADIX + d) : (LbT) 0;
+		}
+	};
+	load_window(0);
+	while (t0 < num_tiles) {
+		/* my chunk: first entry that is not complete (all 32 digit words there), inclusive scan */
+		int fb = C;
+		LbT v[C];
+#pragma unroll
+		for (int u = C - 1; u >= 0; --u)
+			if (!__all_sync(0xffffffffu, (w[u] & PPWord<LbT>::VALID) != 0)) fb = u;
+		LbT acc = 0, tot = 0;
+#pragma unroll
+		for (int u = 0; u < C; ++u) {
+			acc += w[u] & PPWord<LbT>::VAL;
+			v[u] = acc;
+			if (u < fb) tot = acc;
+		}
+		s_tot[(par * WPG + wg) * 32 + lane] = tot;
+		if (lane == 0) s_fb[par * WPG + wg] = fb;
+		asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(WPG * 32) : "memory");
+		/* consumed tiles L = full chunks + the valid part of the first incomplete one */
+		int L = 0;
+		LbT off = 0, consumed = 0;
+		bool open = true;
+#pragma unroll
+		for (int q = 0; q < WPG; ++q) {
+			const int fq = s_fb[par * WPG + q];
+			const LbT tq = s_tot[(par * WPG + q) * 32 + lane];
+			if (open) {
+				L += fq;
+				consumed += tq;
+				if (q < wg) off += tq;
+				if (fq < C) open = false;
+			}
+		}
+		const int my_n = min(max(L - wg * C, 0), C);
+		const u32 my_t = t0 + (u32) (wg * C);
+		/* next window: issued before the stores so that one L2 round trip overlaps them */
+		load_window(t0 + (u32) L);
+		if (L == 0) {
+			if (++idle > (SPIN_LIMIT >> 3)) { atomicExch(err_flag, 1); break; }
+			par ^= 1;
+			continue;
+		}
+#pragma unroll
+		for (int u = 0; u < C; ++u) {
+			if (u < my_n) {
+				const u32 t = my_t + u;
+				st_relaxed(agg + (size_t) t * RADIX + d, (LbT) 0);                         /* consumed: reset */
+				if (t + 1 < num_tiles)
+					st_relaxed(pref + (size_t) (t + 1) * RADIX + d,
+						(LbT) (PPWord<LbT>::VALID | ((running + off + v[u]) & PPWord<LbT>::VAL)));
+			}
+		}
+		running += consumed;
+		t0 += (u32) L;
+		par ^= 1;
+		idle = 0;
+		++rounds;
+	}
+	if (prof_on && threadIdx.x == 0 && cta_index == 0) {
+		atomicAdd(prof + 12, (u64) (clock64() - p_t0));
+		atomicAdd(prof + 13, (u64) rounds);
+	}
+}
+
+template <typename LbT, int THREADS, int G>
+constexpr size_t pp_propagate2_smem() {
+	return (size_t) G * 2 * (THREADS / 32 / G) * 32 * sizeof(LbT) + (size_t) G * 2 * (THREADS / 32 / G) * 4 + 16;
+}
+
 #endif

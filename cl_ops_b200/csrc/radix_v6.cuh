@@ -40,7 +40,61 @@ __device__ __forceinline__ u32 v6_digit(ElemT k, u32 start_bit, u32 dmask) {
 	return ((u32) (((u64) k) >> start_bit)) & dmask;
 }
 
+/* Rare path, kept out of line so that it costs the hot loop no registers.  Tile t (already
+ * written out in a wrong intra-digit order) is ranked again with ballots and scattered
+ * straight to its final positions.  scratch is the tile's own staging buffer ([WARPS][RADIX]
+ * words are used); goff and ds are still those of tile t.  Called by all threads of the CTA. */
 template <typename ElemT, typename LbT, int THREADS, int IPT>
+__device__ __noinline__ void v6_repair(const ElemT* __restrict__ in, ElemT* __restrict__ out, size_t n, u32 t,
+		u32* scratch, const LbT* goff, const u32* ds, u32 start_bit, u32 dmask, int* err_flag) {
+	constexpr int WARPS = THREADS / 32;
+	constexpr int TILE = THREADS * IPT;
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const size_t base = (size_t) t * TILE;
+	const u32 cnt = (base + TILE <= n) ? (u32) TILE : (u32) (n - base);
+	const u32 wbase = (u32) warp * 32u * IPT + lane;
+	if (tid == 0) atomicAdd(err_flag + 1, 1);
+	for (int i = tid; i < WARPS * RADIX; i += THREADS) scratch[i] = 0;
+	__syncthreads();
+	u32* sw = scratch + warp * RADIX;
+	ElemT key[IPT];
+	u32 rank[IPT];
+#pragma unroll 1
+	for (int i = 0; i < IPT; ++i) {
+		const u32 local = wbase + i * 32u;
+		const bool valid = local < cnt;
+		key[i] = valid ? in[base + local] : ElemT(0);
+		const u32 d = v6_digit<ElemT>(key[i], start_bit, dmask);
+		u32 peers = match_digit_ballot(d);
+		peers &= __ballot_sync(0xffffffffu, valid);
+		const u32 lt = peers & lanemask_lt();
+		u32 old = 0;
+		if (valid && lt == 0) { old = sw[d]; sw[d] = old + __popc(peers); }
+		__syncwarp();
+		old = __shfl_sync(0xffffffffu, old, (__ffs(peers) - 1) & 31);
+		rank[i] = old + __popc(lt);
+	}
+	__syncthreads();
+	if (tid < RADIX) {
+		u32 run = 0;
+		for (int w = 0; w < WARPS; ++w) { const u32 c = scratch[w * RADIX + tid]; scratch[w * RADIX + tid] = run; run += c; }
+	}
+	__syncthreads();
+#pragma unroll 1
+	for (int i = 0; i < IPT; ++i) {
+		const u32 local = wbase + i * 32u;
+		if (local < cnt) {
+			const u32 d = v6_digit<ElemT>(key[i], start_bit, dmask);
+			out[goff[d] + (LbT) (ds[d] + sw[d] + rank[i])] = key[i];
+		}
+	}
+	__syncthreads();
+}
+
+const int V6_PROP_GROUPS = 2;                              /* propagator groups (32 digits each) per CTA */
+const int V6_NUM_PROP = RADIX / 32 / V6_PROP_GROUPS;       /* propagator CTAs */
+
+template <typename ElemT, typename LbT, int THREADS, int IPT, int ABL = 0, bool DEEP = true>
 __global__ void __launch_bounds__(THREADS, 2)
 clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, size_t n, u32 num_tiles,
 		LbT* __restrict__ agg, LbT* __restrict__ pref, u32* __restrict__ ticket,
@@ -54,14 +108,36 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
-	if (blockIdx.x < PP_NUM_PROP) {
-		pp_propagate<LbT, THREADS>(agg, pref, num_tiles, err_flag, smem_raw, prof_on);
+	/* The propagators are latency critical; a worker on the same SM puts its shared-memory
+	 * traffic in front of every propagator load.  Each propagator publishes the id of its SM
+	 * and a worker that finds itself on one of them leaves (tiles go by ticket: nothing is lost). */
+	u32* prop_sm = reinterpret_cast<u32*>(err_flag + 48);       /* [PP_NUM_PROP], zeroed per call */
+	u32 my_sm;
+	asm volatile("mov.u32 %0, %%smid;" : "=r"(my_sm));
+	if (blockIdx.x < V6_NUM_PROP) {
+		if (threadIdx.x == 0) st_relaxed(prop_sm + blockIdx.x, my_sm + 1u);
+		pp_propagate2<LbT, THREADS, V6_PROP_GROUPS>(agg, pref, num_tiles, err_flag, smem_raw, prof_on, (int) blockIdx.x);
 		return;
+	}
+	if (flags & 4) {
+		__shared__ int s_leave;
+		if (threadIdx.x == 0) {
+			int leave = 0;
+			for (int k = 0; k < V6_NUM_PROP; ++k) {
+				u32 v = ld_relaxed(prop_sm + k);
+				unsigned spins = 0;
+				while (v == 0 && ++spins < (1u << 20)) v = ld_relaxed(prop_sm + k);
+				if (v == my_sm + 1u) leave = 1;
+			}
+			s_leave = leave;
+		}
+		__syncthreads();
+		if (s_leave) return;
 	}
 
 	u32* whist = reinterpret_cast<u32*>(smem_raw);                          /* [WARPS][RADIX] */
 	u32* s_ds = whist + WARPS * RADIX;                                      /* [2][RADIX] digit starts */
-	u64* s_goff_raw = reinterpret_cast<u64*>(s_ds + 2 * RADIX);             /* [2][RADIX] u64-sized slots */
+	u64* s_goff_raw = reinterpret_cast<u64*>(s_ds + 4 * RADIX);             /* [2][RADIX] u64-sized slots (s_ds has 3 live slots + 1 pad) */
 	u32* s_misc = reinterpret_cast<u32*>(s_goff_raw + 2 * RADIX);           /* [16]: 0..7 scan, 8 ticket, 10..11 bad */
 	ElemT* s_buf = reinterpret_cast<ElemT*>(s_misc + 16);                   /* [2][TILE] */
 
@@ -111,10 +187,10 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	/* coalesced write-out of a staged tile; returns true when the staged order is not
 	 * sorted on the bits processed so far (= some warp instruction's atomics were not
 	 * applied in lane order) */
-	auto write_out = [&](u32 t, int b, bool verify) -> bool {
+	auto write_out = [&](u32 t, int b, int gslot, bool verify) -> bool {
 		const u32 cnt = tile_count_of(t);
 		const ElemT* skeys = s_buf + (size_t) b * TILE;
-		const LbT* goff = goff_of(b);
+		const LbT* goff = goff_of(gslot);
 		bool bad = false;
 		if ((flags & 8) && (t % 5u) == 2u) {
 			/* test hook: write this tile WRONG and report it, so that only a working repair
@@ -130,9 +206,12 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 			for (int i = 0; i < IPT; ++i) {
 				const u32 j = (u32) tid + i * THREADS;
 				const ElemT k = skeys[j];
-				const ElemT kp = skeys[j > 0 ? j - 1 : 0];
-				if ((k & low_mask) < (kp & low_mask)) bad = true;
-				out[goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j] = k;
+				if (ABL != 1) {
+					const ElemT kp = skeys[j > 0 ? j - 1 : 0];
+					if ((k & low_mask) < (kp & low_mask)) bad = true;
+				}
+				const LbT o = goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j;
+				if (ABL != 2 || o == (LbT) ~(LbT) 0) out[o] = k;
 			}
 		} else {
 #pragma unroll
@@ -149,7 +228,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		return verify && bad;
 	};
 	/* prefix threads: PREF[t] -> global offset table of the tile staged in buffer b */
-	auto prefix_to_goff = [&](u32 t, int b, LbT w) {
+	auto prefix_to_goff = [&](u32 t, int gslot, int dslot, LbT w) {
 		const int d = tid - RADIX;
 		LbT* p = pref + (size_t) t * RADIX + d;
 		unsigned spins = 0;
@@ -159,52 +238,11 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		}
 		if (prof_on && d == 0) atomicAdd(prof + 8, (u64) spins);
 		st_relaxed(p, (LbT) 0);                                  /* consumed: reset */
-		goff_of(b)[d] = my_base + (w & PPWord<LbT>::VAL) - (LbT) s_ds[b * RADIX + d];
+		goff_of(gslot)[d] = my_base + (w & PPWord<LbT>::VAL) - (LbT) s_ds[dslot * RADIX + d];
 	};
-	/* Rare path.  Tile t (staged in buffer b, already written out in a wrong intra-digit
-	 * order) is ranked again with ballots and scattered straight to its final positions.
-	 * Uses buffer b as scratch; goff and s_ds of buffer b are still those of tile t.
-	 * Called by all threads between B1 and P2; clobbers key[]. */
-	auto repair = [&](u32 t, int b) {
-		u32* scratch = reinterpret_cast<u32*>(s_buf + (size_t) b * TILE);   /* [WARPS][RADIX] */
-		const u32 cnt = tile_count_of(t);
-		if (tid == 0) atomicAdd(err_flag + 1, 1);
-		for (int i = tid; i < WARPS * RADIX; i += THREADS) scratch[i] = 0;
-		__syncthreads();
-		const size_t base = (size_t) t * TILE;
-		u32* sw = scratch + warp * RADIX;
-		u32 rank[IPT];
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 local = wbase + i * 32u;
-			const bool valid = local < cnt;
-			key[i] = valid ? in[base + local] : ElemT(0);
-			const u32 d = v6_digit<ElemT>(key[i], start_bit, dmask);
-			u32 peers = match_digit_ballot(d);
-			peers &= __ballot_sync(0xffffffffu, valid);
-			const u32 lt = peers & lanemask_lt();
-			u32 old = 0;
-			if (valid && lt == 0) { old = sw[d]; sw[d] = old + __popc(peers); }
-			__syncwarp();
-			old = __shfl_sync(0xffffffffu, old, (__ffs(peers) - 1) & 31);
-			rank[i] = old + __popc(lt);
-		}
-		__syncthreads();
-		if (tid < RADIX) {
-			u32 run = 0;
-			for (int w = 0; w < WARPS; ++w) { const u32 c = scratch[w * RADIX + tid]; scratch[w * RADIX + tid] = run; run += c; }
-		}
-		__syncthreads();
-		const LbT* goff = goff_of(b);
-#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 local = wbase + i * 32u;
-			if (local < cnt) {
-				const u32 d = v6_digit<ElemT>(key[i], start_bit, dmask);
-				out[goff[d] + (LbT) (s_ds[b * RADIX + d] + sw[d] + rank[i])] = key[i];
-			}
-		}
-		__syncthreads();
+	auto repair = [&](u32 t, int b, int gslot, int dslot) {
+		v6_repair<ElemT, LbT, THREADS, IPT>(in, out, n, t, reinterpret_cast<u32*>(s_buf + (size_t) b * TILE),
+			goff_of(gslot), s_ds + dslot * RADIX, start_bit, dmask, err_flag);
 	};
 
 	/* ---- prologue */
@@ -214,13 +252,20 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	u32 cur = s_misc[8];
 	if (cur >= num_tiles) return;
 	load_tile(cur);
-	u32 prev = NONE, pprev = NONE;
-	int b = 0;
-	u32 it = 0;
+	if constexpr (DEEP) {
+	/* ---- schedule with TWO iterations of slack between a tile's AGG and the use of its PREF:
+	 *   P1 count(k) | B1 | P2 digits(k) + PREF(k-2) -> offsets | B2 | write-out(k-2) | B3 |
+	 *   place(k) into the buffer just freed | load(k+1)
+	 * The prefix latency (propagator rounds, L2 round trips, slow neighbours) is then far from
+	 * the critical path and the propagators need no SM of their own.  The next tile's keys
+	 * are pulled into L2 as soon as its ticket is known, so the late load is an L2 hit. */
+	u32 t1 = NONE, t2 = NONE;         /* tiles of the previous two iterations (staged, not yet written) */
+	int b = 0;                        /* buffer of the current tile (= buffer of t2) */
+	int s0 = 0, s1 = 2, s2 = 1;       /* s_ds slots of cur, t1, t2 (k, k-1, k-2 mod 3) */
+	const bool is_pref_thread = tid >= RADIX && tid < 2 * RADIX;
 	for (;;) {
 		LbT wp = 0;
-		const bool is_pref_thread = tid >= RADIX && tid < 2 * RADIX;
-		if (prev != NONE && is_pref_thread) wp = ld_relaxed(pref + (size_t) prev * RADIX + (tid - RADIX));
+		if (t2 != NONE && is_pref_thread) wp = ld_relaxed(pref + (size_t) t2 * RADIX + (tid - RADIX));
 		const u32 cnt = tile_count_of(cur);
 		/* P1 count */
 		if (cnt == (u32) TILE) {
@@ -234,9 +279,116 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		mark(0);
 		__syncthreads();                                         /* B1 */
 		mark(1);
+		/* P2 */
+		if (tid < RADIX) {
+			u32 c[WARPS];
+#pragma unroll
+			for (int w = 0; w < WARPS; ++w) c[w] = whist[w * RADIX + tid];
+			u32 count = 0;
+#pragma unroll
+			for (int w = 0; w < WARPS; ++w) count += c[w];
+			st_relaxed(agg + (size_t) cur * RADIX + tid, (LbT) (PPWord<LbT>::VALID | (LbT) count));
+			const u32 incl = warp_inclusive_scan<u32>(count, lane);
+			if (lane == 31) s_misc[warp] = incl;
+			named_bar_sync(1, RADIX);
+			u32 off = 0;
+#pragma unroll
+			for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[w];
+			u32 run = off + incl - count;
+			s_ds[s0 * RADIX + tid] = run;
+#pragma unroll
+			for (int w = 0; w < WARPS; ++w) { whist[w * RADIX + tid] = run; run += c[w]; }
+		} else if (is_pref_thread) {
+			u32 nt = 0;
+			if (tid == RADIX) nt = atomicAdd(ticket, 1u);        /* in flight during the prefix wait */
+			if (t2 != NONE) prefix_to_goff(t2, 0, s2, wp);
+			if (tid == RADIX) s_misc[8] = nt;
+		}
+		mark(2);
+		__syncthreads();                                         /* B2 */
+		mark(3);
+		const u32 nxt = s_misc[8];
+		const bool more = nxt < num_tiles;
+		if (more) {
+			/* next tile -> L2 (one 128-byte line per thread) */
+			const size_t lo = (size_t) nxt * TILE * sizeof(ElemT) + (size_t) tid * 128;
+			if (lo < n * sizeof(ElemT) && (size_t) tid * 128 < (size_t) TILE * sizeof(ElemT))
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(in) + lo));
+		}
+		/* P5 write-out of the tile staged two iterations ago (same buffer as the current tile) */
+		bool bad = false;
+		if (t2 != NONE) bad = write_out(t2, b, 0, true);
+		mark(4);
+		if (__syncthreads_or(bad ? 1 : 0)) repair(t2, b, 0, s2);   /* B3 */
+		mark(5);
+		/* P3 place + P4 next tile: a key register is refilled as soon as its key is staged */
+		{
+			ElemT* skeys = s_buf + (size_t) b * TILE;
+			const bool next_full = more && tile_count_of(nxt) == (u32) TILE;
+			if (cnt == (u32) TILE && next_full) {
+				const ElemT* np = in + (size_t) nxt * TILE + wbase;
+#pragma unroll
+				for (int i = 0; i < IPT; ++i) {
+					skeys[atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u)] = key[i];
+					key[i] = __ldcs(np + i * 32);
+				}
+				__syncwarp();
+				zero_row();
+			} else {
+#pragma unroll
+				for (int i = 0; i < IPT; ++i)
+					if (wbase + i * 32u < cnt)
+						skeys[atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u)] = key[i];
+				__syncwarp();
+				zero_row();
+				if (more) load_tile(nxt);
+			}
+		}
+		mark(6);
+		t2 = t1; t1 = cur;
+		b ^= 1;
+		{ const int t = s2; s2 = s1; s1 = s0; s0 = t; }
+		if (!more) break;
+		cur = nxt;
+	}
+	/* ---- epilogue: t2 is staged in buffer b, t1 in buffer b^1 */
+	for (int r = 0; r < 2; ++r) {
+		const u32 t = r == 0 ? t2 : t1;
+		const int bb = r == 0 ? b : (b ^ 1);
+		const int ss = r == 0 ? s2 : s1;
+		__syncthreads();
+		if (t == NONE) continue;
+		if (is_pref_thread) prefix_to_goff(t, 0, ss, (LbT) 0);
+		__syncthreads();
+		const bool bad = write_out(t, bb, 0, true);
+		if (__syncthreads_or(bad ? 1 : 0)) repair(t, bb, 0, ss);
+	}
+	} else {
+	u32 prev = NONE, pprev = NONE;
+	int b = 0;
+	u32 it = 0;
+	for (;;) {
+		LbT wp = 0;
+		const bool is_pref_thread = tid >= RADIX && tid < 2 * RADIX;
+		if (prev != NONE && is_pref_thread) wp = ld_relaxed(pref + (size_t) prev * RADIX + (tid - RADIX));
+		const u32 cnt = tile_count_of(cur);
+		/* P1 count */
+		if (cnt == (u32) TILE) {
+			if (ABL != 4) {
+#pragma unroll
+				for (int i = 0; i < IPT; ++i) atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+			}
+		} else {
+#pragma unroll
+			for (int i = 0; i < IPT; ++i)
+				if (wbase + i * 32u < cnt) atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+		}
+		mark(0);
+		__syncthreads();                                         /* B1 */
+		mark(1);
 		/* the write-out of the previous iteration (tile pprev, buffer b) reported a bad order */
 		if (s_misc[10 + ((it + 1) & 1)]) {
-			repair(pprev, b);
+			repair(pprev, b, b, b);
 			load_tile(cur);
 			if (tid == 0) s_misc[10 + ((it + 1) & 1)] = 0;
 		}
@@ -262,7 +414,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		} else if (is_pref_thread) {
 			u32 nt = 0;
 			if (tid == RADIX) nt = atomicAdd(ticket, 1u);        /* in flight during the prefix wait */
-			if (prev != NONE) prefix_to_goff(prev, b ^ 1, wp);
+			if (prev != NONE) prefix_to_goff(prev, b ^ 1, b ^ 1, wp);
 			if (tid == RADIX) s_misc[8] = nt;
 		}
 		mark(2);
@@ -273,8 +425,10 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 			ElemT* skeys = s_buf + (size_t) b * TILE;
 			if (cnt == (u32) TILE) {
 #pragma unroll
-				for (int i = 0; i < IPT; ++i)
-					skeys[atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u)] = key[i];
+				for (int i = 0; i < IPT; ++i) {
+					const u32 p = atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+					if (ABL != 3 || p == 0xffffffffu) skeys[p] = key[i];
+				}
 			} else {
 #pragma unroll
 				for (int i = 0; i < IPT; ++i)
@@ -292,7 +446,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		mark(5);
 		/* P5 write-out of the previous tile */
 		if (prev != NONE) {
-			if (write_out(prev, b ^ 1, true)) s_misc[10 + (it & 1)] = 1;
+			if (write_out(prev, b ^ 1, b ^ 1, true)) s_misc[10 + (it & 1)] = 1;
 		}
 		mark(6);
 		pprev = prev;
@@ -304,18 +458,19 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	}
 	/* ---- epilogue: `prev` is staged in buffer b^1; pprev was written in the last iteration */
 	__syncthreads();
-	if (s_misc[10 + ((it + 1) & 1)]) repair(pprev, b);
-	if (tid >= RADIX && tid < 2 * RADIX) prefix_to_goff(prev, b ^ 1, (LbT) 0);
+	if (s_misc[10 + ((it + 1) & 1)]) repair(pprev, b, b, b);
+	if (tid >= RADIX && tid < 2 * RADIX) prefix_to_goff(prev, b ^ 1, b ^ 1, (LbT) 0);
 	__syncthreads();
-	const bool bad = write_out(prev, b ^ 1, true);
-	if (__syncthreads_or(bad ? 1 : 0)) repair(prev, b ^ 1);
+	const bool bad = write_out(prev, b ^ 1, b ^ 1, true);
+	if (__syncthreads_or(bad ? 1 : 0)) repair(prev, b ^ 1, b ^ 1, b ^ 1);
+	}
 }
 
 template <typename ElemT, int THREADS, int IPT, typename LbT>
 constexpr size_t onesweep_v6_smem() {
-	constexpr size_t worker = (size_t) (THREADS / 32) * RADIX * 4 + 2 * RADIX * 4 + 2 * RADIX * 8 + 16 * 4 +
+	constexpr size_t worker = (size_t) (THREADS / 32) * RADIX * 4 + 4 * RADIX * 4 + 2 * RADIX * 8 + 16 * 4 +
 		2 * (size_t) THREADS * IPT * sizeof(ElemT);
-	constexpr size_t prop = ((size_t) PP_WINDOW * 32 + 8 * 32) * sizeof(LbT) + 16;
+	constexpr size_t prop = pp_propagate2_smem<LbT, THREADS, V6_PROP_GROUPS>();
 	return worker > prop ? worker : prop;
 }
 
