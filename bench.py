@@ -163,10 +163,12 @@ def run_ours(args):
     b_out = clo.Buffer.wrap_tensor(ctx, t_out)
     sorter = clo.CloSort("satradix", ctx, clo.UINT)
     ops = cdist.GpuOps(clo, ctx, queue, clo.UINT) if distributed else None
+    if distributed and os.environ.get("CLO_DIST_EXCHANGE", "fused") == "fused":
+        ops.setup_peer_exchange(n + n // 4, torch.int32, False)
 
     def step():
         if distributed:
-            return cdist.sample_sort(t_in, None, ops, 32)
+            return cdist.sample_sort(t_in, None, ops, 32, gidx0=rank * n)
         sorter.with_device_data(queue, b_in, b_out, n)
         return None
 
@@ -217,7 +219,7 @@ def run_ours(args):
         del u
         dbg = sorter.debug(queue)
     else:
-        k_sorted, _, info = cdist.sample_sort(t_in, None, ops, 32, profile=True)
+        k_sorted, _, info = cdist.sample_sort(t_in, None, ops, 32, profile=True, gidx0=rank * n)
         phases = info.get("phases_ms", {})
         u = k_sorted.to(torch.int64) & 0xFFFFFFFF
         ok = bool((u[1:] >= u[:-1]).all().item()) if u.numel() > 1 else True

@@ -113,6 +113,10 @@ def lib():
         sig("clo_sort_with_host_data", u32, vp, vp, vp, vp, vp, sz, sz, errp)
         sig("clo_sort_pairs_with_device_data", vp, vp, vp, vp, vp, sz, errp)
         sig("clo_sort_partition_with_device_data", vp, vp, vp, vp, vp, vp, vp, sz, u64, vp, vp, u32, vp, errp)
+        sig("clo_sort_partition_count_with_device_data", vp, vp, vp, vp, sz, u64, vp, vp, u32, vp, errp)
+        sig("clo_sort_partition_scatter_with_device_data", vp, vp, vp, vp, vp, sz, u64, vp, vp, u32, vp, vp, vp, vp, errp)
+        sig("clo_b200_ipc_export", u32, vp, ctypes.c_char_p, errp)
+        sig("clo_b200_ipc_import", vp, vp, ctypes.c_char_p, sz, errp)
         sig("clo_sort_b200_debug", u32, vp, vp, ctypes.POINTER(ctypes.c_uint64))
         sig("clo_sort_b200_set_timing", None, vp, u32)
         sig("clo_sort_b200_get_timing", u32, vp, ctypes.POINTER(ctypes.c_float), u32)
@@ -253,6 +257,24 @@ class Buffer:
         e.check()
         return out
 
+    def ipc_export(self):
+        """64-byte CUDA IPC handle of a library-owned buffer (for a peer process on this box)."""
+        out = ctypes.create_string_buffer(64)
+        e = _Err()
+        lib().clo_b200_ipc_export(self.h, out, e.ref())
+        e.check()
+        return out.raw
+
+    @classmethod
+    def ipc_import(cls, ctx, handle, size):
+        """Map a peer process's exported buffer; destroy() unmaps it."""
+        b = cls.__new__(cls)
+        b.ctx, b.size, b._keep = ctx, size, None
+        e = _Err()
+        b.h = lib().clo_b200_ipc_import(ctx.h, ctypes.c_char_p(bytes(handle)), size, e.ref())
+        e.check()
+        return b
+
     def destroy(self):
         if self.h:
             lib().ccl_buffer_destroy(self.h)
@@ -329,6 +351,26 @@ class CloSort:
             payload_out.h if payload_out else None, numel, gidx0,
             splitter_keys.h if splitter_keys else None, splitter_idx.h if splitter_idx else None,
             nparts, counts_out.h, e.ref())
+        e.check()
+        return evt
+
+    def partition_count_with_device_data(self, queue, keys_in, numel, gidx0, splitter_keys, splitter_idx,
+                                         nparts, counts_out):
+        e = _Err()
+        evt = lib().clo_sort_partition_count_with_device_data(
+            self.h, queue.h, keys_in.h, numel, gidx0, splitter_keys.h if splitter_keys else None,
+            splitter_idx.h if splitter_idx else None, nparts, counts_out.h, e.ref())
+        e.check()
+        return evt
+
+    def partition_scatter_with_device_data(self, queue, keys_in, payload_in, numel, gidx0, splitter_keys,
+                                           splitter_idx, nparts, first_slot, dest_ptrs, payload_dest_ptrs, ok_flag):
+        e = _Err()
+        evt = lib().clo_sort_partition_scatter_with_device_data(
+            self.h, queue.h, keys_in.h, payload_in.h if payload_in else None, numel, gidx0,
+            splitter_keys.h if splitter_keys else None, splitter_idx.h if splitter_idx else None, nparts,
+            first_slot.h, dest_ptrs.h, payload_dest_ptrs.h if payload_dest_ptrs else None,
+            ok_flag.h if ok_flag else None, e.ref())
         e.check()
         return evt
 

@@ -46,6 +46,7 @@ struct ccl_buffer {
 	void* ptr;
 	size_t size;
 	bool owns;
+	bool ipc = false;      /* ptr came from cudaIpcOpenMemHandle */
 };
 
 struct ccl_program {
@@ -110,5 +111,19 @@ struct CloScratch {
 	}
 	void release() { if (ptr) cudaFree(ptr); ptr = nullptr; size = 0; }
 };
+
+/* stable multi-way partition by (key, global index) splitters (partition.cu) */
+cudaError_t clo_partition_v2(CloScratch& work, size_t elem_size, const void* keys_in, const uint32_t* payload_in,
+		void* keys_out, uint32_t* payload_out, size_t n, uint64_t gidx0, const void* splitter_keys,
+		const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out, int sm_count, cudaStream_t stream,
+		const char** err_msg);
+
+cudaError_t clo_partition_count_stage(CloScratch& work, size_t elem_size, const void* keys_in, size_t n, uint64_t gidx0,
+		const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out, int sm_count,
+		cudaStream_t stream, const char** err_msg);
+cudaError_t clo_partition_scatter_stage(CloScratch& work, size_t elem_size, const void* keys_in, const uint32_t* payload_in,
+		size_t n, uint64_t gidx0, const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts,
+		const uint64_t* first_slot, void* const* dests, void* const* vdests, const int* ok, int sm_count,
+		cudaStream_t stream, const char** err_msg);
 
 #endif

@@ -1,0 +1,374 @@
+/*
+ * partition.cu -- the sample sort's stable multi-way partition (the
+ * reference is single-device, /root/reference/src/cl_ops/sort/clo_sort_abstract.c:335, so
+ * there is nothing to restate: the contract is the one in include/cl_ops/clo_b200.h).
+ *
+ * With at most 16 buckets there is no need for the radix machinery (tile staging, look-back):
+ *   K1 count    every WARP owns one contiguous chunk of the input and counts its keys per
+ *               bucket (one aggregated shared-memory RED per 32 keys)
+ *   K2 offsets  one CTA per bucket scans the per-warp counts -> each warp's first output
+ *               slot in every bucket, and the bucket totals (counts_out)
+ *   K3 scatter  every warp walks its chunk again; a key's slot is
+ *               bucket start + warp offset + running count + rank among the lower lanes,
+ *               the rank coming from one ballot per bucket.  Lanes of a bucket write
+ *               consecutive addresses, instruction after instruction, so the partial
+ *               sectors merge in L2.
+ * HBM traffic: 2 reads + 1 write of the keys (12 B per u32 key), no atomics on global memory.
+ * Stable: chunks are in input order, a warp walks its chunk in order, ranks follow lane order.
+ */
+#include "clo_internal.h"
+#include "device_utils.cuh"
+#include "sort_common.h"
+
+#include <type_traits>
+
+using namespace clo;
+
+namespace {
+
+const int PT_THREADS = 256;
+const int PT_WARPS = PT_THREADS / 32;
+const int PT_MAXP = 16;
+const int PT_U = 8;                       /* independent 128-byte loads in flight per warp */
+
+/* NS = number of splitter slots compiled in (1, 3, 7 or 15); slots past the real splitters
+ * hold (max key, max index), which no element reaches, so they never count */
+template <typename ElemT, int NS> struct PtSplitters {
+	ElemT key[NS];
+	u64 idx[NS];
+	u64 gidx0;                            /* global index of element 0 */
+};
+
+/* the splitters are tiny and device resident: every thread pulls them into registers */
+template <typename ElemT, int NS>
+__device__ __forceinline__ void pt_load_splitters(PtSplitters<ElemT, NS>& sp, const ElemT* __restrict__ sk,
+		const u64* __restrict__ si, u32 count, u64 gidx0) {
+	sp.gidx0 = gidx0;
+#pragma unroll
+	for (int s = 0; s < NS; ++s) {
+		sp.key[s] = s < (int) count ? sk[s] : (ElemT) ~(ElemT) 0;
+		sp.idx[s] = s < (int) count ? si[s] : ~0ull;
+	}
+}
+
+/* bucket = number of splitters (key, index) <= (k, g).  The index only matters for a key
+ * that EQUALS a splitter key, so the 64-bit tie-break runs only when some lane needs it. */
+template <typename ElemT, int NS>
+__device__ __forceinline__ u32 pt_bucket(ElemT k, u64 g, const PtSplitters<ElemT, NS>& sp) {
+	u32 b = 0;
+	bool tie = false;
+#pragma unroll
+	for (int s = 0; s < NS; ++s) {
+		b += sp.key[s] < k ? 1u : 0u;
+		tie |= sp.key[s] == k;
+	}
+	if (__any_sync(__activemask(), tie)) {
+#pragma unroll
+		for (int s = 0; s < NS; ++s) b += (sp.key[s] == k && sp.idx[s] <= g) ? 1u : 0u;
+	}
+	return b;
+}
+
+/* chunk of warp w: [w * chunk, min(n, (w + 1) * chunk)), chunk a multiple of 32 * PT_U */
+template <typename ElemT, int NS>
+__global__ void __launch_bounds__(PT_THREADS)
+clo_partition_count(const ElemT* __restrict__ in, size_t n, size_t chunk, u32 total_warps,
+		const ElemT* __restrict__ sk, const u64* __restrict__ si, u32 nsplit, u64 gidx0,
+		u32* __restrict__ counts /* [PT_MAXP][total_warps] */) {
+	__shared__ u32 sh[PT_WARPS][PT_MAXP];
+	PtSplitters<ElemT, NS> sp;
+	pt_load_splitters<ElemT, NS>(sp, sk, si, nsplit, gidx0);
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 w = blockIdx.x * PT_WARPS + warp;
+	if (lane < PT_MAXP) sh[warp][lane] = 0;
+	__syncwarp();
+	const size_t lo = (size_t) w * chunk;
+	const size_t hi = lo + chunk < n ? lo + chunk : n;
+	for (size_t base = lo; base < hi; base += 32 * PT_U) {
+		ElemT k[PT_U];
+#pragma unroll
+		for (int u = 0; u < PT_U; ++u) {
+			const size_t i = base + u * 32 + lane;
+			k[u] = i < hi ? __ldcs(in + i) : ElemT(0);
+		}
+#pragma unroll
+		for (int u = 0; u < PT_U; ++u) {
+			const size_t i = base + u * 32 + lane;
+			if (i < hi) atomicAdd(&sh[warp][pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp)], 1u);
+		}
+	}
+	__syncwarp();
+	if (lane < PT_MAXP && w < total_warps) counts[(size_t) lane * total_warps + w] = sh[warp][lane];
+}
+
+/* block q: exclusive scan of counts[q][*] in place (-> warp offsets inside bucket q) and the
+ * bucket total */
+__global__ void __launch_bounds__(1024)
+clo_partition_offsets(u32* __restrict__ counts, u32 total_warps, u64* __restrict__ totals,
+		u64* __restrict__ counts_out, u32 nparts) {
+	__shared__ u64 s_w[32];
+	__shared__ u64 s_run;
+	const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	u32* row = counts + (size_t) blockIdx.x * total_warps;
+	if (t == 0) s_run = 0;
+	__syncthreads();
+	for (u32 base = 0; base < total_warps; base += 1024) {
+		const u32 i = base + t;
+		const u64 c = i < total_warps ? row[i] : 0;
+		const u64 incl = warp_inclusive_scan<u64>(c, lane);
+		if (lane == 31) s_w[warp] = incl;
+		__syncthreads();
+		u64 off = s_run;
+		for (int v = 0; v < warp; ++v) off += s_w[v];
+		/* offsets inside a bucket fit 32 bits (n < 2^32 is checked by the host side) */
+		if (i < total_warps) row[i] = (u32) (off + incl - c);
+		__syncthreads();
+		if (t == 1023) s_run = off + incl;
+		__syncthreads();
+	}
+	if (t == 0) {
+		totals[blockIdx.x] = s_run;
+		if (counts_out && blockIdx.x < nparts) counts_out[blockIdx.x] = s_run;
+	}
+}
+
+/* local mode: every bucket goes to the same output array, bucket after bucket */
+__global__ void clo_partition_local_slots(const u64* __restrict__ totals, u64* __restrict__ first_slot,
+		void** __restrict__ dests, void** __restrict__ vdests, void* out, void* vout) {
+	const int q = threadIdx.x;
+	if (q < PT_MAXP) {
+		u64 run = 0;
+		for (int p = 0; p < q; ++p) run += totals[p];
+		first_slot[q] = run;
+		dests[q] = out;
+		vdests[q] = vout;
+	}
+}
+
+/* Bucket q of this rank goes to dests[q] (possibly PEER memory, written over NVLink) starting
+ * at element first_slot[q].  Keys are not written as they come (a warp instruction would give
+ * each bucket a 16-64 byte fragment, which NVLink and the L2 handle badly): every warp keeps a
+ * 64-element ring per bucket in shared memory and writes a bucket only in whole, 128-byte
+ * ALIGNED lines of 32 elements (the first write of a bucket is short so that the following ones
+ * are aligned; the last one drains the ring).  Lane q carries the state of bucket q.
+ * *ok == 0 (a receive buffer would overflow) turns the kernel into a no-op. */
+template <typename ElemT, bool HAS_VAL, int NS, int SW /* warps per CTA */>
+__global__ void __launch_bounds__(SW * 32)
+clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin, size_t n, size_t chunk, u32 total_warps,
+		const ElemT* __restrict__ sk, const u64* __restrict__ si, u32 nsplit, u64 gidx0,
+		const u32* __restrict__ offsets /* [PT_MAXP][total_warps] */, const u64* __restrict__ first_slot,
+		ElemT* const* __restrict__ dests, u32* const* __restrict__ vdests, const int* __restrict__ ok, u32 nparts) {
+	constexpr int NB = NS + 1;
+	__shared__ ElemT s_key[SW][NB][64];
+	__shared__ u32 s_val[HAS_VAL ? SW : 1][HAS_VAL ? NB : 1][HAS_VAL ? 64 : 1];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const u32 w = blockIdx.x * SW + warp;
+	if (w >= total_warps) return;
+	if (ok && *ok == 0) return;
+	PtSplitters<ElemT, NS> sp;
+	pt_load_splitters<ElemT, NS>(sp, sk, si, nsplit, gidx0);
+	ElemT* kp = nullptr;          /* next element of bucket `lane` to be written */
+	u32* vp = nullptr;
+	u32 head = 0, cnt = 0;        /* ring of bucket `lane`: first pending slot, pending elements */
+	if (lane < (int) nparts) {
+		const u64 slot = first_slot[lane] + offsets[(size_t) lane * total_warps + w];
+		kp = dests[lane] + slot;
+		if (HAS_VAL) vp = vdests[lane] + slot;
+	}
+	ElemT (*ring)[64] = s_key[warp];
+	const size_t lo = (size_t) w * chunk;
+	const size_t hi = lo + chunk < n ? lo + chunk : n;
+	const u32 lt = lanemask_lt();
+	/* write f pending elements of bucket q (state in lane q) */
+	auto flush = [&](int q, u32 f) {
+		const u32 h = __shfl_sync(0xffffffffu, head, q);
+		ElemT* dk = reinterpret_cast<ElemT*>(__shfl_sync(0xffffffffu, (u64) reinterpret_cast<uintptr_t>(kp), q));
+		if ((u32) lane < f) dk[lane] = ring[q][(h + lane) & 63];
+		if (HAS_VAL) {
+			u32* dv = reinterpret_cast<u32*>(__shfl_sync(0xffffffffu, (u64) reinterpret_cast<uintptr_t>(vp), q));
+			if ((u32) lane < f) dv[lane] = s_val[HAS_VAL ? warp : 0][HAS_VAL ? q : 0][HAS_VAL ? ((h + lane) & 63) : 0];
+		}
+		if (lane == q) { head = (head + f) & 63; cnt -= f; kp += f; if (HAS_VAL) vp += f; }
+	};
+	for (size_t base = lo; base < hi; base += 32 * PT_U) {
+		ElemT k[PT_U];
+		u32 v[HAS_VAL ? PT_U : 1];
+#pragma unroll
+		for (int u = 0; u < PT_U; ++u) {
+			const size_t i = base + u * 32 + lane;
+			k[u] = i < hi ? __ldcs(in + i) : ElemT(0);
+			if (HAS_VAL) v[u] = i < hi ? __ldcs(vin + i) : 0u;
+		}
+#pragma unroll
+		for (int u = 0; u < PT_U; ++u) {
+			const size_t i = base + u * 32 + lane;
+			const bool valid = i < hi;
+			u32 b = pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp);
+			if (!valid) b = 0xffffffffu;
+			u32 mine = 0, add = 0;
+#pragma unroll
+			for (u32 q = 0; q < (u32) NB; ++q) {
+				const u32 m = __ballot_sync(0xffffffffu, b == q);
+				if (b == q) mine = m;
+				if ((u32) lane == q) add = __popc(m);
+			}
+			/* append to the ring of my bucket */
+			const u32 tail = __shfl_sync(0xffffffffu, head + cnt, valid ? (int) b : 0);
+			if (valid) {
+				const u32 slot = (tail + __popc(mine & lt)) & 63;
+				ring[b][slot] = k[u];
+				if (HAS_VAL) s_val[HAS_VAL ? warp : 0][HAS_VAL ? b : 0][HAS_VAL ? slot : 0] = v[u];
+			}
+			cnt += add;
+			__syncwarp();
+			/* buckets that can fill a line up to the next 128-byte boundary */
+			for (;;) {
+				const u32 mis = (u32) ((reinterpret_cast<uintptr_t>(kp) & 127) / sizeof(ElemT));
+				const u32 thr = 32u - mis;
+				u32 need = __ballot_sync(0xffffffffu, lane < NB && cnt >= thr);
+				if (!need) break;
+				while (need) {
+					const int q = __ffs(need) - 1;
+					need &= need - 1;
+					flush(q, __shfl_sync(0xffffffffu, thr, q));
+				}
+				__syncwarp();
+			}
+		}
+	}
+	/* drain */
+	for (int q = 0; q < NB; ++q) {
+		u32 left = __shfl_sync(0xffffffffu, cnt, q);
+		while (left) {
+			const u32 f = left < 32u ? left : 32u;
+			flush(q, f);
+			left -= f;
+		}
+	}
+}
+
+struct PtPlan { size_t chunk; u32 total_warps, grid; u32* counts; u64* totals; u64* first_slot; void** dests; void** vdests; };
+
+cudaError_t pt_plan(CloScratch& work, size_t n, int sm_count, PtPlan& pl) {
+	const u32 ctas = (u32) sm_count * 8;
+	u32 total_warps = ctas * PT_WARPS;
+	size_t chunk = (n + total_warps - 1) / total_warps;
+	const size_t gran = 32 * PT_U;
+	chunk = (chunk + gran - 1) / gran * gran;
+	if (chunk == 0) chunk = gran;
+	/* the warp count is a function of sm_count only, so the count and scatter stages of one
+	 * partition (and the scratch they share) always agree; idle warps have empty chunks */
+	pl.chunk = chunk;
+	pl.total_warps = total_warps;
+	pl.grid = ctas;
+	const size_t cnt_bytes = ((size_t) PT_MAXP * total_warps * sizeof(u32) + 255) / 256 * 256;
+	cudaError_t e = work.reserve(cnt_bytes + 4 * 256);
+	if (e != cudaSuccess) return e;
+	char* base = (char*) work.ptr;
+	pl.counts = (u32*) base;
+	pl.totals = (u64*) (base + cnt_bytes);
+	pl.first_slot = (u64*) (base + cnt_bytes + 256);
+	pl.dests = (void**) (base + cnt_bytes + 512);
+	pl.vdests = (void**) (base + cnt_bytes + 768);
+	return cudaSuccess;
+}
+
+template <typename ElemT>
+cudaError_t pt_count_typed(CloScratch& work, const ElemT* in, size_t n, u64 gidx0, const void* sk, const u64* si,
+		u32 nparts, u64* counts_out, int sm_count, cudaStream_t stream) {
+	PtPlan pl;
+	cudaError_t e = pt_plan(work, n, sm_count, pl);
+	if (e != cudaSuccess) return e;
+	const ElemT* dsk = (const ElemT*) sk;
+	const u32 nsplit = nparts - 1;
+	auto run = [&](auto ns_tag) {
+		constexpr int NS = decltype(ns_tag)::value;
+		clo_partition_count<ElemT, NS><<<pl.grid, PT_THREADS, 0, stream>>>(in, n, pl.chunk, pl.total_warps, dsk, si, nsplit, gidx0, pl.counts);
+	};
+	if (nsplit <= 1) run(std::integral_constant<int, 1>{});
+	else if (nsplit <= 3) run(std::integral_constant<int, 3>{});
+	else if (nsplit <= 7) run(std::integral_constant<int, 7>{});
+	else run(std::integral_constant<int, 15>{});
+	clo_partition_offsets<<<PT_MAXP, 1024, 0, stream>>>(pl.counts, pl.total_warps, pl.totals, counts_out, nparts);
+	CLO_COUNT_LAUNCH(2);
+	return cudaGetLastError();
+}
+
+template <typename ElemT>
+cudaError_t pt_scatter_typed(CloScratch& work, const ElemT* in, const u32* vin, size_t n, u64 gidx0, const void* sk,
+		const u64* si, u32 nparts, const u64* first_slot, void* const* dests, void* const* vdests, const int* ok,
+		int sm_count, cudaStream_t stream) {
+	PtPlan pl;
+	cudaError_t e = pt_plan(work, n, sm_count, pl);
+	if (e != cudaSuccess) return e;
+	const ElemT* dsk = (const ElemT*) sk;
+	const u32 nsplit = nparts - 1;
+	auto run = [&](auto ns_tag) {
+		constexpr int NS = decltype(ns_tag)::value;
+		/* the rings of 16 buckets need 48 KB for 4 warps: smaller CTAs there */
+		constexpr int SW = NS > 7 ? 4 : PT_WARPS;
+		const u32 grid = (pl.total_warps + SW - 1) / SW;
+		if (vin)
+			clo_partition_scatter<ElemT, true, NS, SW><<<grid, SW * 32, 0, stream>>>(in, vin, n, pl.chunk, pl.total_warps, dsk, si, nsplit, gidx0,
+				pl.counts, first_slot, (ElemT* const*) dests, (u32* const*) vdests, ok, nparts);
+		else
+			clo_partition_scatter<ElemT, false, NS, SW><<<grid, SW * 32, 0, stream>>>(in, vin, n, pl.chunk, pl.total_warps, dsk, si, nsplit, gidx0,
+				pl.counts, first_slot, (ElemT* const*) dests, (u32* const*) vdests, ok, nparts);
+	};
+	if (nsplit <= 1) run(std::integral_constant<int, 1>{});
+	else if (nsplit <= 3) run(std::integral_constant<int, 3>{});
+	else if (nsplit <= 7) run(std::integral_constant<int, 7>{});
+	else run(std::integral_constant<int, 15>{});
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
+}
+
+bool pt_args_ok(size_t elem_size, size_t n, uint32_t nparts, const char** err_msg) {
+	if (nparts < 1 || nparts > (uint32_t) PT_MAXP) { if (err_msg) *err_msg = "partition: nparts must be in [1,16]"; return false; }
+	if (n >= (1ull << 32)) { if (err_msg) *err_msg = "partition: too many elements"; return false; }
+	if (elem_size != 4 && elem_size != 8) { if (err_msg) *err_msg = "partition: keys must be 4 or 8 bytes"; return false; }
+	return true;
+}
+
+} // namespace
+
+/* stage 1: bucket sizes of this rank -> counts_out[nparts] (device); keeps the per-warp
+ * offsets in `work` for stage 2 (same n, same device) */
+cudaError_t clo_partition_count_stage(CloScratch& work, size_t elem_size, const void* keys_in, size_t n, uint64_t gidx0,
+		const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out, int sm_count,
+		cudaStream_t stream, const char** err_msg) {
+	if (!pt_args_ok(elem_size, n, nparts, err_msg)) return cudaErrorInvalidValue;
+	if (elem_size == 4)
+		return pt_count_typed<u32>(work, (const u32*) keys_in, n, gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, sm_count, stream);
+	return pt_count_typed<u64>(work, (const u64*) keys_in, n, gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, sm_count, stream);
+}
+
+/* stage 2: scatter bucket q to dests[q] + first_slot[q] (device arrays of nparts entries;
+ * the destinations may be peer memory) */
+cudaError_t clo_partition_scatter_stage(CloScratch& work, size_t elem_size, const void* keys_in, const uint32_t* payload_in,
+		size_t n, uint64_t gidx0, const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts,
+		const uint64_t* first_slot, void* const* dests, void* const* vdests, const int* ok, int sm_count,
+		cudaStream_t stream, const char** err_msg) {
+	if (!pt_args_ok(elem_size, n, nparts, err_msg)) return cudaErrorInvalidValue;
+	if (elem_size == 4)
+		return pt_scatter_typed<u32>(work, (const u32*) keys_in, payload_in, n, gidx0, splitter_keys, (const u64*) splitter_idx, nparts,
+			(const u64*) first_slot, dests, vdests, ok, sm_count, stream);
+	return pt_scatter_typed<u64>(work, (const u64*) keys_in, payload_in, n, gidx0, splitter_keys, (const u64*) splitter_idx, nparts,
+		(const u64*) first_slot, dests, vdests, ok, sm_count, stream);
+}
+
+cudaError_t clo_partition_v2(CloScratch& work, size_t elem_size, const void* keys_in, const uint32_t* payload_in,
+		void* keys_out, uint32_t* payload_out, size_t n, uint64_t gidx0, const void* splitter_keys,
+		const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out, int sm_count, cudaStream_t stream,
+		const char** err_msg) {
+	cudaError_t e = clo_partition_count_stage(work, elem_size, keys_in, n, gidx0, splitter_keys, splitter_idx, nparts,
+		counts_out, sm_count, stream, err_msg);
+	if (e != cudaSuccess) return e;
+	PtPlan pl;
+	if ((e = pt_plan(work, n, sm_count, pl)) != cudaSuccess) return e;
+	clo_partition_local_slots<<<1, 32, 0, stream>>>(pl.totals, pl.first_slot, pl.dests, pl.vdests, keys_out, payload_out);
+	CLO_COUNT_LAUNCH(1);
+	if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	return clo_partition_scatter_stage(work, elem_size, keys_in, payload_in, n, gidx0, splitter_keys, splitter_idx, nparts,
+		(const uint64_t*) pl.first_slot, pl.dests, pl.vdests, nullptr, sm_count, stream, err_msg);
+}

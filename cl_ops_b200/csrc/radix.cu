@@ -930,12 +930,46 @@ cudaError_t partition_typed(CloRadixState* st, const ElemT* in, const u32* vin, 
 
 } // namespace
 
+static int clo_current_sm_count() {
+	int dev = 0, sms = 0;
+	cudaGetDevice(&dev);
+	if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+	return sms;
+}
+
+cudaError_t clo_radix_partition_count(CloRadixState* st, size_t elem_size, const void* keys_in, size_t n, uint64_t gidx0,
+		const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out,
+		cudaStream_t stream, const char** err_msg) {
+	return clo_partition_count_stage(st->work, elem_size, keys_in, n, gidx0, splitter_keys, splitter_idx, nparts,
+		counts_out, clo_current_sm_count(), stream, err_msg);
+}
+
+cudaError_t clo_radix_partition_scatter(CloRadixState* st, size_t elem_size, const void* keys_in, const uint32_t* payload_in,
+		size_t n, uint64_t gidx0, const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts,
+		const uint64_t* first_slot, void* const* dests, void* const* vdests, const int* ok,
+		cudaStream_t stream, const char** err_msg) {
+	return clo_partition_scatter_stage(st->work, elem_size, keys_in, payload_in, n, gidx0, splitter_keys, splitter_idx,
+		nparts, first_slot, dests, vdests, ok, clo_current_sm_count(), stream, err_msg);
+}
+
 cudaError_t clo_radix_partition(CloRadixState* st, size_t elem_size, const void* keys_in,
 		const uint32_t* payload_in, void* keys_out, uint32_t* payload_out, size_t n, uint64_t gidx0,
 		const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out,
 		cudaStream_t stream, const char** err_msg) {
 	if (nparts < 1 || nparts > 16) { if (err_msg) *err_msg = "partition: nparts must be in [1,16]"; return cudaErrorInvalidValue; }
 	if (n >= (1ull << 40)) { if (err_msg) *err_msg = "partition: too many elements"; return cudaErrorInvalidValue; }
+	{
+		/* default: the chunk-per-warp partition (partition.cu); CLO_PARTITION=onesweep keeps the
+		 * splitter-as-digit onesweep variant below */
+		const char* pk = getenv("CLO_PARTITION");
+		if (!(pk && strcmp(pk, "onesweep") == 0) && n < (1ull << 32)) {
+			int dev = 0, sms = 0;
+			cudaGetDevice(&dev);
+			if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+			return clo_partition_v2(st->work, elem_size, keys_in, payload_in, keys_out, payload_out, n, gidx0,
+				splitter_keys, splitter_idx, nparts, counts_out, sms, stream, err_msg);
+		}
+	}
 	const bool has_val = payload_in != nullptr;
 	if (elem_size == 4) {
 		if (has_val) return partition_typed<u32, true>(st, (const u32*) keys_in, payload_in, (u32*) keys_out, payload_out, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);

@@ -308,9 +308,38 @@ extern "C" void ccl_buffer_destroy(CCLBuffer* buf) {
 	if (buf->owns && buf->ptr) {
 		CloDeviceGuard g(buf->ctx->dev.ordinal);
 		cudaFree(buf->ptr);
+	} else if (buf->ipc && buf->ptr) {
+		CloDeviceGuard g(buf->ctx->dev.ordinal);
+		cudaIpcCloseMemHandle(buf->ptr);
 	}
 	ccl_context_unref(buf->ctx);
 	delete buf;
+}
+
+/* ---- peer memory of another process on the same box (one process per GPU): the receive
+ *      buffers of the sample sort are exported once and written by the peers' scatter kernels */
+extern "C" cl_bool clo_b200_ipc_export(CCLBuffer* buf, unsigned char handle[64], GError** err) {
+	if (!buf || !buf->owns || !handle) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "ipc export: need a buffer created by ccl_buffer_new"); return CL_FALSE; }
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+	CloDeviceGuard g(buf->ctx->dev.ordinal);
+	cudaIpcMemHandle_t h;
+	if (clo_cuda_failed(cudaIpcGetMemHandle(&h, buf->ptr), err, "cudaIpcGetMemHandle")) return CL_FALSE;
+	memcpy(handle, &h, 64);
+	return CL_TRUE;
+}
+
+extern "C" CCLBuffer* clo_b200_ipc_import(CCLContext* ctx, const unsigned char handle[64], size_t size, GError** err) {
+	if (!ctx || !handle) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "ipc import: NULL argument"); return NULL; }
+	CloDeviceGuard g(ctx->dev.ordinal);
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	void* p = NULL;
+	if (clo_cuda_failed(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), err, "cudaIpcOpenMemHandle")) return NULL;
+	ccl_buffer* b = new ccl_buffer();
+	b->refs = 1; b->ctx = ctx; b->ptr = p; b->size = size; b->owns = false; b->ipc = true;
+	ccl_context_ref(ctx);
+	clo_handle_add(b);
+	return b;
 }
 
 extern "C" size_t ccl_memobj_get_size(CCLMemObj* mo, GError** err) { (void) err; return mo ? mo->size : 0; }

@@ -610,3 +610,59 @@ extern "C" CCLEvent* clo_sort_partition_with_device_data(CloSort* sorter, CCLQue
 	if (clo_cuda_failed(rc, err, "clo_radix_partition")) return NULL;
 	return evt;
 }
+
+/* Sample sort, fused partition + exchange: stage 1 (bucket sizes) and stage 2 (scatter into
+ * the receive buffers of the destination ranks).  dest_ptrs / payload_dest_ptrs are device
+ * arrays of nparts raw device addresses (own buffer or peer memory imported with
+ * clo_b200_ipc_import); first_slot[q] is the element index in destination q at which this
+ * rank's bucket starts; *ok_flag == 0 makes the scatter a no-op (receive buffer too small). */
+extern "C" CCLEvent* clo_sort_partition_count_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+		CCLBuffer* keys_in, size_t numel, cl_ulong gidx0, CCLBuffer* splitter_keys, CCLBuffer* splitter_idx,
+		cl_uint nparts, CCLBuffer* counts_out, GError** err) {
+	if (!sorter || (err && *err) || !cq_exec) return NULL;
+	const size_t kb = clo_type_sizeof(sorter->elem_type);
+	if (!keys_in || !counts_out || keys_in->size < numel * kb || counts_out->size < nparts * sizeof(cl_ulong) ||
+			(nparts > 1 && (!splitter_keys || !splitter_idx || splitter_keys->size < (nparts - 1) * kb ||
+				splitter_idx->size < (nparts - 1) * sizeof(cl_ulong)))) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "partition count: invalid buffers");
+		return NULL;
+	}
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_partition_count");
+	const char* msg = NULL;
+	cudaError_t rc = clo_radix_partition_count(sorter->rs, kb, keys_in->ptr, numel, gidx0,
+		splitter_keys ? splitter_keys->ptr : NULL, splitter_idx ? (const uint64_t*) splitter_idx->ptr : NULL,
+		nparts, (uint64_t*) counts_out->ptr, cq_exec->stream, &msg);
+	clo_queue_end(cq_exec, evt);
+	if (rc != cudaSuccess && msg) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg); return NULL; }
+	if (clo_cuda_failed(rc, err, "clo_partition_count")) return NULL;
+	return evt;
+}
+
+extern "C" CCLEvent* clo_sort_partition_scatter_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+		CCLBuffer* keys_in, CCLBuffer* payload_in, size_t numel, cl_ulong gidx0, CCLBuffer* splitter_keys,
+		CCLBuffer* splitter_idx, cl_uint nparts, CCLBuffer* first_slot, CCLBuffer* dest_ptrs,
+		CCLBuffer* payload_dest_ptrs, CCLBuffer* ok_flag, GError** err) {
+	if (!sorter || (err && *err) || !cq_exec) return NULL;
+	const size_t kb = clo_type_sizeof(sorter->elem_type);
+	if (!keys_in || !first_slot || !dest_ptrs || keys_in->size < numel * kb ||
+			first_slot->size < nparts * sizeof(cl_ulong) || dest_ptrs->size < nparts * sizeof(void*) ||
+			(payload_in && (!payload_dest_ptrs || payload_dest_ptrs->size < nparts * sizeof(void*))) ||
+			(nparts > 1 && (!splitter_keys || !splitter_idx))) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "partition scatter: invalid buffers");
+		return NULL;
+	}
+	CloDeviceGuard g(cq_exec->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq_exec, "clo_partition_scatter");
+	const char* msg = NULL;
+	cudaError_t rc = clo_radix_partition_scatter(sorter->rs, kb, keys_in->ptr,
+		payload_in ? (const uint32_t*) payload_in->ptr : NULL, numel, gidx0,
+		splitter_keys ? splitter_keys->ptr : NULL, splitter_idx ? (const uint64_t*) splitter_idx->ptr : NULL, nparts,
+		(const uint64_t*) first_slot->ptr, (void* const*) dest_ptrs->ptr,
+		payload_dest_ptrs ? (void* const*) payload_dest_ptrs->ptr : NULL, ok_flag ? (const int*) ok_flag->ptr : NULL,
+		cq_exec->stream, &msg);
+	clo_queue_end(cq_exec, evt);
+	if (rc != cudaSuccess && msg) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg); return NULL; }
+	if (clo_cuda_failed(rc, err, "clo_partition_scatter")) return NULL;
+	return evt;
+}

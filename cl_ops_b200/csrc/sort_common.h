@@ -101,4 +101,15 @@ cudaError_t clo_bitonic_sort(CloBitonicState* st, size_t elem_size, const CloKey
 cudaError_t clo_gselect_sort(size_t elem_size, const CloKeySpec& ks, const void* in, void* out,
 	size_t n, cudaStream_t stream);
 
+/* the two stages of the partition, for the fused partition + exchange of the sample sort:
+ * count -> (the ranks exchange their bucket sizes) -> scatter straight into the receive
+ * buffers of the destination ranks (dests[q] may be peer memory) */
+cudaError_t clo_radix_partition_count(CloRadixState* st, size_t elem_size, const void* keys_in, size_t n, uint64_t gidx0,
+		const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts, uint64_t* counts_out,
+		cudaStream_t stream, const char** err_msg);
+cudaError_t clo_radix_partition_scatter(CloRadixState* st, size_t elem_size, const void* keys_in, const uint32_t* payload_in,
+		size_t n, uint64_t gidx0, const void* splitter_keys, const uint64_t* splitter_idx, uint32_t nparts,
+		const uint64_t* first_slot, void* const* dests, void* const* vdests, const int* ok,
+		cudaStream_t stream, const char** err_msg);
+
 #endif

@@ -24,6 +24,7 @@ import torch
 import torch.distributed as dist
 
 _SIGN64 = -0x8000000000000000
+_I64_MAX = 0x7FFFFFFFFFFFFFFF
 
 
 def _unsigned_order_i64(keys, key_bits):
@@ -33,12 +34,20 @@ def _unsigned_order_i64(keys, key_bits):
     return keys.to(torch.int64) ^ _SIGN64
 
 
+class _DevMem:
+    """library-owned device memory seen as a torch tensor (zero copy, __cuda_array_interface__)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 class GpuOps:
     """Local operators on CUDA tensors through the C-ABI (cl_ops_b200.lib())."""
 
     def __init__(self, clo, ctx, queue, key_type):
         self.clo, self.ctx, self.queue, self.key_type = clo, ctx, queue, key_type
         self.sorter = clo.CloSort("satradix", ctx, key_type)
+        self.peer = None
 
     def _buf(self, t):
         return self.clo.Buffer.wrap_tensor(self.ctx, t)
@@ -73,23 +82,88 @@ class GpuOps:
         bk.destroy()
         return keys, payload
 
+    # ---- fused partition + exchange over peer memory (one process per GPU, one box)
+    def setup_peer_exchange(self, capacity, key_dtype, with_payload, group=None):
+        """Allocate this rank's receive buffers (capacity elements), export them with CUDA IPC
+        and map every peer's: afterwards the partition's scatter kernel writes each bucket
+        straight into its destination rank over NVLink.  Collective; call once."""
+        P, r = dist.get_world_size(group), dist.get_rank(group)
+        kb = torch.empty(0, dtype=key_dtype).element_size()
+        own = [self.clo.Buffer(self.ctx, size=max(1, capacity) * kb)]
+        if with_payload:
+            own.append(self.clo.Buffer(self.ctx, size=max(1, capacity) * 4))
+        handles = [None] * P
+        dist.all_gather_object(handles, [b.ipc_export() for b in own], group=group)
+        maps = []
+        for i in range(P):
+            maps.append(own if i == r else
+                        [self.clo.Buffer.ipc_import(self.ctx, h, b.size) for h, b in zip(handles[i], own)])
+        dev = torch.device("cuda", torch.cuda.current_device())
+        ptrs = torch.zeros(2, 16, dtype=torch.int64)
+        for i in range(P):
+            for j, b in enumerate(maps[i]):
+                ptrs[j, i] = b.ptr
+        self.peer = {
+            "P": P, "r": r, "capacity": capacity, "own": own, "maps": maps, "ptrs": ptrs.to(dev),
+            "recv_k": torch.as_tensor(_DevMem(own[0].ptr, own[0].size), device=dev).view(key_dtype),
+            "recv_p": torch.as_tensor(_DevMem(own[1].ptr, own[1].size), device=dev).view(torch.int32) if with_payload else None,
+            "with_payload": with_payload, "group": group,
+        }
+        dist.barrier(group=group)
+
+    def partition_count(self, keys, gidx0, splitter_keys, splitter_idx, nparts):
+        counts = torch.zeros(nparts, dtype=torch.int64, device=keys.device)
+        bk, bc = self._buf(keys), self._buf(counts)
+        bsk = self._buf(splitter_keys) if nparts > 1 else None
+        bsi = self._buf(splitter_idx) if nparts > 1 else None
+        self.sorter.partition_count_with_device_data(self.queue, bk, keys.numel(), gidx0, bsk, bsi, nparts, bc)
+        for b in (bk, bc, bsk, bsi):
+            if b is not None:
+                b.destroy()
+        return counts
+
+    def partition_scatter(self, keys, payload, gidx0, splitter_keys, splitter_idx, nparts, first_slot, ok):
+        pe = self.peer
+        bk = self._buf(keys)
+        bp = self._buf(payload) if payload is not None else None
+        bsk = self._buf(splitter_keys) if nparts > 1 else None
+        bsi = self._buf(splitter_idx) if nparts > 1 else None
+        bfs, bok = self._buf(first_slot), self._buf(ok)
+        bd = self._buf(pe["ptrs"][0])
+        bpd = self._buf(pe["ptrs"][1]) if payload is not None else None
+        self.sorter.partition_scatter_with_device_data(self.queue, bk, bp, keys.numel(), gidx0, bsk, bsi, nparts,
+                                                       bfs, bd, bpd, bok)
+        for b in (bk, bp, bsk, bsi, bfs, bok, bd, bpd):
+            if b is not None:
+                b.destroy()
+
+    def sort_received(self, n_recv):
+        """stable sort of the first n_recv received elements into fresh tensors (the receive
+        buffers themselves are overwritten by the peers in the next exchange)"""
+        pe = self.peer
+        if pe["with_payload"]:
+            k, p = self.sort(pe["recv_k"][:n_recv], pe["recv_p"][:n_recv])
+            return k.clone(), p.clone()
+        out = torch.empty(n_recv, dtype=pe["recv_k"].dtype, device=pe["recv_k"].device)
+        if n_recv:
+            bi, bo = self._buf(pe["recv_k"][:n_recv]), self._buf(out)
+            self.sorter.with_device_data(self.queue, bi, bo, n_recv)
+            bi.destroy(); bo.destroy()
+        return out, None
+
     def close(self):
+        if self.peer:
+            dist.barrier(group=self.peer["group"])
+            for i, bl in enumerate(self.peer["maps"]):
+                if i != self.peer["r"]:
+                    for b in bl:
+                        b.destroy()
+            self.peer["recv_k"] = self.peer["recv_p"] = None
+            dist.barrier(group=self.peer["group"])
+            for b in self.peer["own"]:
+                b.destroy()
+            self.peer = None
         self.sorter.destroy()
-
-
-def choose_splitters(sample_keys_i64, sample_idx, nparts):
-    """P-1 splitters from the gathered samples: lexicographic (key, global index) order,
-    regular positions.  `sample_keys_i64` is in unsigned-order int64 form."""
-    total = sample_keys_i64.numel()
-    # lexicographic sort: stable sort by index, then stable sort by key
-    o1 = torch.argsort(sample_idx, stable=True)
-    k1 = sample_keys_i64[o1]
-    o2 = torch.argsort(k1, stable=True)
-    order = o1[o2]
-    pos = torch.tensor([(k * total) // nparts for k in range(1, nparts)], dtype=torch.int64,
-                       device=sample_keys_i64.device)
-    sel = order[pos]
-    return sel
 
 
 class _Phases:
@@ -112,13 +186,44 @@ class _Phases:
                 for i in range(len(self.marks) - 1)}
 
 
-def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None, profile=False):
+def _exchange(src, dst, send_list, recv_list, r, P, group):
+    """all-to-all-v of contiguous buckets.  The rank's own bucket never touches NCCL (a
+    device-local copy); the others go as one group of NCCL sends and receives over NVLink
+    (CLO_DIST_EXCHANGE=a2a selects the single all_to_all_single call instead)."""
+    import os
+    if os.environ.get("CLO_DIST_EXCHANGE") == "a2a" or not src.is_cuda:
+        dist.all_to_all_single(dst, src, output_split_sizes=recv_list, input_split_sizes=send_list, group=group)
+        return
+    so = [0] * (P + 1)
+    ro = [0] * (P + 1)
+    for i in range(P):
+        so[i + 1] = so[i] + send_list[i]
+        ro[i + 1] = ro[i] + recv_list[i]
+    ops = []
+    for k in range(1, P):
+        to, fr = (r + k) % P, (r - k) % P
+        if send_list[to]:
+            ops.append(dist.P2POp(dist.isend, src[so[to]:so[to + 1]], dist.get_global_rank(group, to) if group else to, group=group))
+        if recv_list[fr]:
+            ops.append(dist.P2POp(dist.irecv, dst[ro[fr]:ro[fr + 1]], dist.get_global_rank(group, fr) if group else fr, group=group))
+    works = dist.batch_isend_irecv(ops) if ops else []
+    dst[ro[r]:ro[r + 1]].copy_(src[so[r]:so[r + 1]])
+    for w in works:
+        w.wait()
+
+
+def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None, profile=False, gidx0=None):
     """Globally stable sort of the concatenation of every rank's `keys` (rank order).
 
     keys: 1-D int32 (u32 bit pattern) or int64 (u64 bit pattern) tensor on this rank.
     payload: optional int32 tensor, moved with the keys.
+    gidx0: global index of this rank's first element when the caller knows it (saves one
+    host synchronisation); None = derive it from the gathered element counts.
     Returns (keys, payload, info): rank r ends up with the r-th slice of the sorted
     sequence (slice lengths differ slightly between ranks).
+
+    Host synchronisations per call: one (the bucket sizes NCCL needs as host integers), plus
+    one more when gidx0 is not given.
     """
     P = dist.get_world_size(group)
     r = dist.get_rank(group)
@@ -127,46 +232,80 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None,
     ph = _Phases(profile and keys.is_cuda)
     ph.mark("start")
 
-    # global index of my first element (ranks may hold different counts)
-    n_all = torch.zeros(P, dtype=torch.int64, device=dev)
-    n_all[r] = n_local
-    dist.all_reduce(n_all, group=group)
-    gidx0 = int(n_all[:r].sum().item())
-
     if P == 1:
         k, p = ops.sort(keys, payload)
         return k, p, {"sent": 0, "received": n_local, "gidx0": 0}
 
-    # 1) regular samples of the unsorted local data, with their global indices
-    s = samples_per_rank or 64 * P
-    s = max(1, min(s, n_local)) if n_local > 0 else 0
-    smax = torch.tensor([s], dtype=torch.int64, device=dev)
-    dist.all_reduce(smax, op=dist.ReduceOp.MAX, group=group)
-    smax = int(smax.item())
-    samp_k = torch.zeros(smax, dtype=torch.int64, device=dev)
-    samp_i = torch.full((smax,), -1, dtype=torch.int64, device=dev)   # -1 marks padding
+    # 1) regular samples of the unsorted local data.  One all-gather carries, per rank:
+    #    [n_local, s, sample keys (cap), sample positions (cap)]; global indices are formed
+    #    after the gather from the gathered counts, so nothing has to come back to the host.
+    cap = samples_per_rank or 64 * P
+    s = min(cap, n_local)
+    row = torch.zeros(2 + 2 * cap, dtype=torch.int64, device=dev)
+    row[0] = n_local
+    row[1] = s
     if s > 0:
         pos = (torch.arange(s, dtype=torch.int64, device=dev) * n_local) // s
-        samp_k[:s] = _unsigned_order_i64(keys[pos], key_bits)
-        samp_i[:s] = gidx0 + pos
-    all_k = torch.empty(P * smax, dtype=torch.int64, device=dev)
-    all_i = torch.empty(P * smax, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(all_k, samp_k, group=group)
-    dist.all_gather_into_tensor(all_i, samp_i, group=group)
-    valid = all_i >= 0
-    all_k, all_i = all_k[valid], all_i[valid]
-
+        row[2:2 + s] = _unsigned_order_i64(keys[pos], key_bits)
+        row[2 + cap:2 + cap + s] = pos
+    allr = torch.empty(P * (2 + 2 * cap), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(allr, row, group=group)
+    allr = allr.view(P, 2 + 2 * cap)
+    n_all = allr[:, 0]
+    g0_all = torch.cumsum(n_all, 0) - n_all
+    if gidx0 is None:
+        gidx0 = int(g0_all[r].item())
     ph.mark("samples+allgather")
-    # 2) splitters (identical on every rank: same data, same deterministic procedure)
-    sel = choose_splitters(all_k, all_i, P)
+
+    # 2) splitters (identical on every rank: same data, same deterministic procedure).
+    #    The gathered samples are already in global-index order (rank, then position), so ONE
+    #    stable sort by key gives the lexicographic (key, index) order; unused slots carry the
+    #    largest key and sort behind everything.  All on the device: no host round trip.
+    valid = torch.arange(cap, dtype=torch.int64, device=dev)[None, :] < allr[:, 1:2]
+    all_k = torch.where(valid, allr[:, 2:2 + cap], _I64_MAX).reshape(-1)
+    all_i = (allr[:, 2 + cap:] + g0_all[:, None]).reshape(-1)
+    order = torch.argsort(all_k, stable=True)
+    total = allr[:, 1].sum()
+    pick = (torch.arange(1, P, dtype=torch.int64, device=dev) * total) // P
+    sel = order[pick]
     spl_k64, spl_i = all_k[sel], all_i[sel]
     if key_bits == 32:
         spl_keys = spl_k64.to(torch.int32)            # low 32 bits = the raw u32 pattern
     else:
         spl_keys = spl_k64 ^ _SIGN64
     spl_keys, spl_i = spl_keys.contiguous(), spl_i.contiguous()
-
     ph.mark("splitters")
+
+    # 3+4 fused) count -> all-gather of the P x P bucket sizes -> every bucket is scattered
+    #    straight into the receive buffer of its destination rank (peer memory, NVLink)
+    pe = getattr(ops, "peer", None)
+    if pe is not None and pe["with_payload"] == (payload is not None):
+        counts = ops.partition_count(keys, gidx0, spl_keys, spl_i, P)
+        ph.mark("count")
+        M = torch.empty(P * P, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(M, counts, group=group)
+        M = M.view(P, P)                                   # M[src][dst]
+        first_slot = torch.zeros(16, dtype=torch.int64, device=dev)
+        first_slot[:P] = (torch.cumsum(M, 0) - M)[r]
+        col = M.sum(0)
+        ok = (col <= pe["capacity"]).all().to(torch.int32).reshape(1)
+        ph.mark("sizes all-gather")
+        ops.partition_scatter(keys, payload, gidx0, spl_keys, spl_i, P, first_slot, ok)
+        ph.mark("scatter to peers")
+        done = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(done, group=group)                 # every peer's writes have landed
+        host = torch.cat([M[:, r], M[r], ok.to(torch.int64)]).tolist()   # the one host synchronisation
+        recv_list, send_list, fits = host[:P], host[P:2 * P], bool(host[2 * P])
+        ph.mark("barrier+sizes to host")
+        if fits:
+            n_recv = sum(recv_list)
+            out_k, out_p = ops.sort_received(n_recv)
+            ph.mark("local sort")
+            info = {"sent": n_local - send_list[r], "received": n_recv, "gidx0": gidx0, "fused": True,
+                    "send_counts": send_list, "recv_counts": recv_list, "phases_ms": ph.result()}
+            return out_k, out_p, info
+        # a receive buffer would overflow (nothing was written): fall through to the NCCL path
+
     # 3) stable local partition into P buckets; bucket sizes
     part_k, part_p, counts = ops.partition(keys, payload, gidx0, spl_keys, spl_i, P)
     ph.mark("partition")
@@ -174,17 +313,17 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None,
     # 4) exchange: counts, then the buckets (all-to-all-v)
     recv_counts = torch.empty_like(counts)
     dist.all_to_all_single(recv_counts, counts, group=group)
-    send_list = [int(x) for x in counts.tolist()]
-    recv_list = [int(x) for x in recv_counts.tolist()]
+    both = torch.stack([counts, recv_counts]).tolist()          # the one host synchronisation
+    send_list = [int(x) for x in both[0]]
+    recv_list = [int(x) for x in both[1]]
     n_recv = sum(recv_list)
+    ph.mark("counts")
     recv_k = torch.empty(n_recv, dtype=keys.dtype, device=dev)
-    dist.all_to_all_single(recv_k, part_k, output_split_sizes=recv_list, input_split_sizes=send_list,
-                           group=group)
-    recv_p = None
+    recv_p = torch.empty(n_recv, dtype=payload.dtype, device=dev) if payload is not None else None
+    ph.mark("alloc")
+    _exchange(part_k, recv_k, send_list, recv_list, r, P, group)
     if payload is not None:
-        recv_p = torch.empty(n_recv, dtype=payload.dtype, device=dev)
-        dist.all_to_all_single(recv_p, part_p, output_split_sizes=recv_list, input_split_sizes=send_list,
-                               group=group)
+        _exchange(part_p, recv_p, send_list, recv_list, r, P, group)
 
     ph.mark("exchange")
     # 5) stable local sort of what arrived (chunks are in source-rank order, each in its

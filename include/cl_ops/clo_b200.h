@@ -61,6 +61,25 @@ CCLEvent* clo_sort_partition_with_device_data(CloSort* sorter, CCLQueue* cq_exec
 	CCLBuffer* splitter_keys, CCLBuffer* splitter_idx, cl_uint nparts,
 	CCLBuffer* counts_out, GError** err);
 
+/* Sample sort, fused partition + exchange (one process per GPU on one box):
+ * stage 1 counts this rank's buckets; the ranks exchange the sizes; stage 2 scatters every
+ * bucket straight into the receive buffer of its destination rank over NVLink.
+ * dest_ptrs / payload_dest_ptrs: device arrays of nparts raw device addresses (own buffer or
+ * peer memory from clo_b200_ipc_import); first_slot[q]: element index in destination q where
+ * this rank's bucket q starts; *ok_flag == 0 makes the scatter a no-op. */
+CCLEvent* clo_sort_partition_count_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+	CCLBuffer* keys_in, size_t numel, cl_ulong gidx0, CCLBuffer* splitter_keys,
+	CCLBuffer* splitter_idx, cl_uint nparts, CCLBuffer* counts_out, GError** err);
+CCLEvent* clo_sort_partition_scatter_with_device_data(CloSort* sorter, CCLQueue* cq_exec,
+	CCLBuffer* keys_in, CCLBuffer* payload_in, size_t numel, cl_ulong gidx0,
+	CCLBuffer* splitter_keys, CCLBuffer* splitter_idx, cl_uint nparts, CCLBuffer* first_slot,
+	CCLBuffer* dest_ptrs, CCLBuffer* payload_dest_ptrs, CCLBuffer* ok_flag, GError** err);
+
+/* CUDA IPC for buffers created by ccl_buffer_new: export a 64-byte handle, import it in
+ * another process of the same box (peer access is enabled on first use). */
+cl_bool clo_b200_ipc_export(CCLBuffer* buf, unsigned char handle[64], GError** err);
+CCLBuffer* clo_b200_ipc_import(CCLContext* ctx, const unsigned char handle[64], size_t size, GError** err);
+
 /* Status words of the sorter's last radix call (blocks on the queue): out[0] look-back
  * timeout flag, out[1] number of tiles whose atomic ranks failed verification and were
  * redone with the ballot ranks, out[2..17] optional phase profile (CLO_RADIX_PROFILE=1). */
