@@ -183,6 +183,8 @@ def run_ours(args):
 
     # ---- timed region: K steps, device time, per-kernel events for the roofline
     sorter.set_timing(True)
+    if distributed:
+        ops.sorter.set_timing(True)
     launches0 = clo.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -193,18 +195,19 @@ def run_ours(args):
     for k in range(args.steps):
         step()
         ev[k + 1].record()
-        if not distributed:
-            # reading the per-kernel events blocks on the step that just ran; the next step's
-            # launch gap is outside every kernel's own duration
-            tm = sorter.get_timing()
-            if len(tm) >= 2:
-                hist_ms.append(tm[0])
-                pass_ms.extend(tm[1:])
+        # reading the per-kernel events blocks on the step that just ran; the next step's
+        # launch gap is outside every kernel's own duration
+        tm = (ops.sorter if distributed else sorter).get_timing()
+        if len(tm) >= 2:
+            hist_ms.append(tm[0])
+            pass_ms.extend(tm[1:])
     barrier()
     clocks = sampler.stop()
     launches = clo.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[args.steps])
     sorter.set_timing(False)
+    if distributed:
+        ops.sorter.set_timing(False)
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -239,10 +242,10 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
     e2e = None
-    if rank == 0:
-        e2e_steps = max(1, min(3, args.steps))
-        h_in = torch.empty(n, dtype=torch.int32).pin_memory()
-        h_in.copy_(t_in.cpu())
+    e2e_steps = max(1, min(3, args.steps))
+    h_in = torch.empty(n, dtype=torch.int32).pin_memory()
+    h_in.copy_(t_in.cpu())
+    if not distributed:
         h_out = torch.empty(n, dtype=torch.int32).pin_memory()
         e2e_sorter = clo.CloSort("satradix", ctx, clo.UINT)
 
@@ -260,7 +263,36 @@ def run_ours(args):
                "ms_per_step": dt * 1e3, "steps": e2e_steps, "n_gpus": 1,
                "api": "clo_sort_with_host_data (pinned host buffers, device alloc + H2D + sort + D2H per call)"}
         e2e_sorter.destroy()
-        del h_in, h_out
+        del h_out
+    else:
+        # every rank: its shard host -> device, the sample sort, its slice of the result device -> host
+        h_out = torch.empty(n + n // 4, dtype=torch.int32).pin_memory()
+        d_in = torch.empty(n, dtype=torch.int32, device="cuda")
+
+        def e2e_step():
+            d_in.copy_(h_in, non_blocking=True)
+            k, _, _ = cdist.sample_sort(d_in, None, ops, 32, gidx0=rank * n)
+            h_out[:k.numel()].copy_(k, non_blocking=True)
+            torch.cuda.synchronize()
+            return k.numel()
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        got = 0
+        for _ in range(e2e_steps):
+            got = e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / e2e_steps
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        ho = h_out.numpy().view(np.uint32)[:got]
+        assert bool(np.all(ho[1:] >= ho[:-1]))
+        e2e = {"value": world * n / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 4 * n * world,
+               "d2h_bytes_per_step": 4 * n * world, "ms_per_step": dt * 1e3, "steps": e2e_steps, "n_gpus": world,
+               "api": "per rank: pinned host shard -> device, cl_ops_b200.dist.sample_sort, sorted slice -> pinned host; max over ranks"}
+        del h_out, d_in
+    del h_in
 
     # ---- CPU baseline beside it (rank 0, N == 1 only): bounded sample
     cpu = None
@@ -276,11 +308,12 @@ def run_ours(args):
         if pass_ms:
             avg = float(np.mean(pass_ms))
             ach = BYTES_PER_KEY_PASS * n / avg / 1e6
-            roof = {"bound": "hbm", "kernel": "clo_radix_onesweep", "achieved": ach, "peak": peak, "unit": "GB/s",
+            roof = {"bound": "hbm", "kernel": "clo_radix_onesweep_v6", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": BYTES_PER_KEY_PASS * n, "avg_launch_ms": avg,
                     "launches_timed": len(pass_ms), "histogram_ms": float(np.mean(hist_ms)),
                     "share_of_step": 4 * avg / ms_per_step,
+                    "note": "per GPU: the onesweep passes of the local sort (rank 0)" if distributed else None,
                     "whole_sort": {"achieved": BYTES_PER_KEY * n / ms_per_step / 1e6,
                                    "frac": BYTES_PER_KEY * n / ms_per_step / 1e6 / peak, "bytes_per_key": BYTES_PER_KEY}}
             try:
@@ -303,7 +336,15 @@ def run_ours(args):
         }
         if distributed:
             out["phases_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
-            out["exchange"] = {"sent_keys_rank0": info["sent"], "received_keys_rank0": info["received"]}
+            sc = phases.get("scatter to peers")
+            out["exchange"] = {"sent_keys_rank0": info["sent"], "received_keys_rank0": info["received"],
+                               "fused_peer_scatter": bool(info.get("fused"))}
+            if sc:
+                # NVLink roofline of the exchange: bytes this rank pushes to its peers / the
+                # duration of the fused partition-scatter kernel that pushes them
+                out["exchange"].update({"remote_bytes_rank0": 4 * info["sent"], "scatter_ms": sc,
+                                        "nvlink_gbs": 4 * info["sent"] / sc / 1e6, "nvlink_peak_gbs": 900.0,
+                                        "nvlink_frac": 4 * info["sent"] / sc / 1e6 / 900.0})
         print(json.dumps(out))
     b_in.destroy(); b_out.destroy(); sorter.destroy()
     if ops:

@@ -222,3 +222,105 @@ def test_sort_errors(clo, ctx):
     s = clo.CloSort("satradix", ctx, oracle.UINT)
     assert s.kernel_names() == ["clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep"]
     s.destroy()
+
+
+@pytest.mark.parametrize("et", [oracle.UINT, oracle.ULONG])
+def test_satradix_atomic_rank_repair_path(clo, ctx, queue, et, monkeypatch):
+    """The keys-only onesweep kernel ranks with shared-memory atomics and VERIFIES every tile it
+    writes; CLO_RADIX_PP_FLAGS=8 makes every fifth tile be written wrong and reported, so the
+    result is only sorted if the ballot-rank repair path works."""
+    monkeypatch.setenv("CLO_RADIX_PP_FLAGS", "8")
+    rng = np.random.default_rng(77 + et)
+    n = (1 << 20) + 4321
+    a = _rand(rng, et, n)
+    a[: n // 3] &= 0xFFFF                      # duplicates in the upper digits
+    s = clo.CloSort("satradix", ctx, et)
+    got = s.with_host_data(a, queue)
+    dbg = s.debug(queue)
+    s.destroy()
+    monkeypatch.delenv("CLO_RADIX_PP_FLAGS")
+    clo.CloSort("satradix", ctx, et).destroy()   # re-reads the environment: flag off again
+    assert np.array_equal(got, np.sort(a))
+    assert dbg[0] == 0 and dbg[1] > 0          # no timeout; tiles were repaired
+
+
+@pytest.mark.parametrize("et,P,with_payload", [(oracle.UINT, 2, False), (oracle.ULONG, 4, True),
+                                               (oracle.UINT, 16, True), (oracle.ULONG, 3, False)])
+def test_partition_stages_scatter_to_destinations(clo, ctx, queue, et, P, with_payload):
+    """Fused partition + exchange building blocks: stage 1 counts, stage 2 scatters bucket q to
+    dests[q] + first_slot[q] (here: one tensor per bucket, standing in for the peers' receive
+    buffers).  Stable inside every bucket; *ok == 0 writes nothing."""
+    import torch
+    rng = np.random.default_rng(100 + P)
+    dt = oracle.NP_TYPES[et]
+    n, g0 = 200003, 5_000_000_000
+    keys = rng.integers(0, 40, size=n).astype(dt)
+    payload = np.arange(n, dtype=np.uint32)
+    sk = np.sort(rng.integers(0, 40, size=P - 1)).astype(dt)
+    si = (g0 + np.sort(rng.integers(0, n, size=P - 1))).astype(np.uint64)
+    o = np.lexsort((si, sk)); sk, si = sk[o], si[o]
+    g = g0 + np.arange(n, dtype=np.uint64)
+    bucket = np.zeros(n, dtype=np.int64)
+    for k_, i_ in zip(sk, si):
+        bucket += ((k_ < keys) | ((k_ == keys) & (i_ <= g))).astype(np.int64)
+    tdt = torch.int32 if dt().itemsize == 4 else torch.int64
+    sdt = np.int32 if dt().itemsize == 4 else np.int64
+    tk = torch.from_numpy(keys.view(sdt)).cuda()
+    tp = torch.from_numpy(payload.view(np.int32)).cuda()
+    tsk = torch.from_numpy(sk.view(sdt)).cuda()
+    tsi = torch.from_numpy(si.view(np.int64)).cuda()
+    cnt = torch.zeros(P, dtype=torch.int64, device="cuda")
+    s = clo.CloSort("satradix", ctx, et)
+    W = clo.Buffer.wrap_tensor
+    b = [W(ctx, tk), W(ctx, tsk), W(ctx, tsi), W(ctx, cnt), W(ctx, tp)]
+    s.partition_count_with_device_data(queue, b[0], n, g0, b[1], b[2], P, b[3])
+    queue.finish()
+    want_cnt = np.bincount(bucket, minlength=P)
+    assert np.array_equal(cnt.cpu().numpy(), want_cnt)
+    lead = [int(x) for x in rng.integers(0, 100, size=P)]          # unaligned first slots
+    dk = [torch.full((lead[q] + int(want_cnt[q]) + 64,), -1, dtype=tdt, device="cuda") for q in range(P)]
+    dp = [torch.full((lead[q] + int(want_cnt[q]) + 64,), -1, dtype=torch.int32, device="cuda") for q in range(P)]
+    ptr_k = torch.zeros(16, dtype=torch.int64); ptr_p = torch.zeros(16, dtype=torch.int64)
+    for q in range(P):
+        ptr_k[q], ptr_p[q] = dk[q].data_ptr(), dp[q].data_ptr()
+    ptr_k, ptr_p = ptr_k.cuda(), ptr_p.cuda()
+    fs = torch.zeros(16, dtype=torch.int64); fs[:P] = torch.tensor(lead); fs = fs.cuda()
+    for okv in (0, 1):
+        ok = torch.tensor([okv], dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        bb = [W(ctx, fs), W(ctx, ptr_k), W(ctx, ptr_p), W(ctx, ok)]
+        s.partition_scatter_with_device_data(queue, b[0], b[4] if with_payload else None, n, g0, b[1], b[2], P,
+                                             bb[0], bb[1], bb[2] if with_payload else None, bb[3])
+        queue.finish()
+        for x in bb:
+            x.destroy()
+        for q in range(P):
+            got = dk[q].cpu().numpy().view(dt)
+            c = int(want_cnt[q])
+            if okv == 0:
+                assert np.all(dk[q].cpu().numpy() == -1)                  # no-op
+                continue
+            assert np.array_equal(got[lead[q]:lead[q] + c], keys[bucket == q])    # stable
+            assert np.all(dk[q].cpu().numpy()[:lead[q]] == -1) and np.all(dk[q].cpu().numpy()[lead[q] + c:] == -1)
+            if with_payload:
+                assert np.array_equal(dp[q].cpu().numpy().view(np.uint32)[lead[q]:lead[q] + c], payload[bucket == q])
+    for x in b:
+        x.destroy()
+    s.destroy()
+
+
+def test_sample_sort_two_gpus_fused_exchange():
+    """2 ranks, one per GPU: fused partition + peer-memory exchange + local sort equals the
+    stable sort of the concatenated input (skipped on a one-GPU box)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "dist_gpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DIST GPU OK" in r.stdout
