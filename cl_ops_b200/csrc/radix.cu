@@ -755,7 +755,7 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		u32* vnxt = to_dst ? vdst : vaux;
 		u32* ticket = L.tickets + p;
 		bool done_v6 = false;
-		if constexpr (!HAS_VAL && IDENTITY && sizeof(ElemT) >= 4 && THREADS >= 2 * RADIX) {
+		if constexpr (!HAS_VAL && IDENTITY && sizeof(ElemT) >= 4 && THREADS > RADIX) {
 			if (use_pp && st->kernel_v6) {
 				char* agg = (char*) st->pp.ptr;
 				char* pref = agg + tiles * RADIX * (wide ? 8 : 4);

@@ -164,15 +164,15 @@ __device__ __forceinline__ void pp_propagate(LbT* __restrict__ agg, LbT* __restr
  * in registers and publishes only its chunk total -- no window-wide shared-memory scan, one
  * barrier per round.  Same protocol and invariant as pp_propagate:
  * at the top of a round AGG of tiles < t0 is consumed (reset), PREF of tiles <= t0 published. */
-const int PP2_WINDOW = 128;
+const int PP2_CHUNK = 16;                   /* tiles per warp and round; window = warps per group x 16 */
 
 template <typename LbT, int THREADS, int G>
 __device__ __forceinline__ void pp_propagate2(LbT* __restrict__ agg, LbT* __restrict__ pref, u32 num_tiles,
 		int* __restrict__ err_flag, unsigned char* smem_raw, int prof_on, int cta_index) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int WPG = WARPS / G;                 /* warps per group */
-	constexpr int C = PP2_WINDOW / WPG;            /* tiles per warp and round */
-	static_assert(WARPS % G == 0 && PP2_WINDOW % WPG == 0, "bad propagator shape");
+	constexpr int C = PP2_CHUNK;                   /* tiles per warp and round */
+	static_assert(WARPS % G == 0, "bad propagator shape");
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int grp = warp / WPG, wg = warp % WPG;
 	/* shared: per group, double buffered: fb[WPG] ints + tot[WPG][32] LbT */

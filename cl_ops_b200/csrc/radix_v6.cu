@@ -35,6 +35,7 @@ cudaError_t launch_v6(int tile, const ElemT* in, ElemT* out, size_t n, LbT* agg,
 	}
 	const size_t tiles = (n + (size_t) tile - 1) / (size_t) tile;
 	size_t workers = (size_t) sm_count * ctas_per_sm[dev];
+	constexpr int V6_NUM_PROP = v6_num_prop(THREADS);
 	workers = workers > (size_t) V6_NUM_PROP ? workers - V6_NUM_PROP : 1;
 	if (workers > tiles) workers = tiles;
 	kern<<<(unsigned) (V6_NUM_PROP + workers), THREADS, SMEM, stream>>>(in, out, n, (u32) tiles,

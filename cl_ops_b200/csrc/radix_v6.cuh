@@ -91,11 +91,12 @@ __device__ __noinline__ void v6_repair(const ElemT* __restrict__ in, ElemT* __re
 	__syncthreads();
 }
 
-const int V6_PROP_GROUPS = 2;                              /* propagator groups (32 digits each) per CTA */
-const int V6_NUM_PROP = RADIX / 32 / V6_PROP_GROUPS;       /* propagator CTAs */
+/* propagator groups (32 digits each) per CTA and propagator CTAs, by CTA size */
+__host__ __device__ constexpr int v6_prop_groups(int threads) { return threads >= 512 ? 2 : 1; }
+__host__ __device__ constexpr int v6_num_prop(int threads) { return RADIX / 32 / v6_prop_groups(threads); }
 
 template <typename ElemT, typename LbT, int THREADS, int IPT, int ABL = 0, bool DEEP = true>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 3 : 2))
 clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, size_t n, u32 num_tiles,
 		LbT* __restrict__ agg, LbT* __restrict__ pref, u32* __restrict__ ticket,
 		const u64* __restrict__ bins_base, u32 start_bit, u32 dmask,
@@ -103,10 +104,40 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	constexpr int WARPS = THREADS / 32;
 	constexpr int TILE = THREADS * IPT;
 	constexpr u32 NONE = 0xffffffffu;
-	static_assert(THREADS >= 2 * RADIX, "256 digit threads + 256 prefix threads");
+	static_assert(THREADS > RADIX && RADIX % (THREADS - RADIX) == 0, "256 digit threads + prefix threads owning whole digits");
+	constexpr int PREF_T = THREADS - RADIX;        /* prefix threads */
+	constexpr int DPT = RADIX / PREF_T;            /* digits per prefix thread */
 	static_assert((size_t) TILE * sizeof(ElemT) >= (size_t) WARPS * RADIX * 4, "repair scratch lives in a staging buffer");
 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
+
+	/* A pass whose digit is the same for every key is the identity permutation (keys that are
+	 * small, already grouped, or all equal): the global histogram says so up front, and the
+	 * whole grid then just copies its tiles -- no ranking, no prefix traffic. */
+	{
+		__shared__ int s_trivial;
+		if (threadIdx.x == 0) s_trivial = 0;
+		__syncthreads();
+		if (threadIdx.x < RADIX) {
+			const u64 hi = threadIdx.x + 1 < RADIX ? bins_base[threadIdx.x + 1] : (u64) n;
+			if (hi - bins_base[threadIdx.x] == (u64) n) s_trivial = 1;
+		}
+		__syncthreads();
+		if (s_trivial) {
+			constexpr int NP = v6_num_prop(THREADS);
+			if (blockIdx.x < NP) return;
+			const u32 wb = (u32) (threadIdx.x >> 5) * 32u * IPT + (threadIdx.x & 31);
+			for (u32 t = blockIdx.x - NP; t < num_tiles; t += gridDim.x - NP) {
+				const size_t base = (size_t) t * TILE;
+#pragma unroll
+				for (int i = 0; i < IPT; ++i) {
+					const size_t j = base + wb + i * 32u;
+					if (j < n) out[j] = __ldcs(in + j);
+				}
+			}
+			return;
+		}
+	}
 
 	/* The propagators are latency critical; a worker on the same SM puts its shared-memory
 	 * traffic in front of every propagator load.  Each propagator publishes the id of its SM
@@ -114,6 +145,8 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	u32* prop_sm = reinterpret_cast<u32*>(err_flag + 48);       /* [PP_NUM_PROP], zeroed per call */
 	u32 my_sm;
 	asm volatile("mov.u32 %0, %%smid;" : "=r"(my_sm));
+	constexpr int V6_PROP_GROUPS = v6_prop_groups(THREADS);
+	constexpr int V6_NUM_PROP = v6_num_prop(THREADS);
 	if (blockIdx.x < V6_NUM_PROP) {
 		if (threadIdx.x == 0) st_relaxed(prop_sm + blockIdx.x, my_sm + 1u);
 		pp_propagate2<LbT, THREADS, V6_PROP_GROUPS>(agg, pref, num_tiles, err_flag, smem_raw, prof_on, (int) blockIdx.x);
@@ -146,7 +179,9 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	const u32 wbase = (u32) warp * 32u * IPT + lane;
 	u32* wh = whist + warp * RADIX;
 	/* the prefix threads own one digit each */
-	const LbT my_base = tid >= RADIX && tid < 2 * RADIX ? (LbT) bins_base[tid - RADIX] : (LbT) 0;
+	LbT my_base[DPT];
+#pragma unroll
+	for (int j = 0; j < DPT; ++j) my_base[j] = tid >= RADIX ? (LbT) bins_base[tid - RADIX + j * PREF_T] : (LbT) 0;
 
 	ElemT key[IPT];
 
@@ -228,17 +263,21 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		return verify && bad;
 	};
 	/* prefix threads: PREF[t] -> global offset table of the tile staged in buffer b */
-	auto prefix_to_goff = [&](u32 t, int gslot, int dslot, LbT w) {
-		const int d = tid - RADIX;
-		LbT* p = pref + (size_t) t * RADIX + d;
-		unsigned spins = 0;
-		while (!(w & PPWord<LbT>::VALID)) {
-			if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
-			w = ld_relaxed(p);
+	auto prefix_to_goff = [&](u32 t, int gslot, int dslot, const LbT (&w0)[DPT]) {
+#pragma unroll
+		for (int j = 0; j < DPT; ++j) {
+			const int d = tid - RADIX + j * PREF_T;
+			LbT* p = pref + (size_t) t * RADIX + d;
+			LbT w = w0[j];
+			unsigned spins = 0;
+			while (!(w & PPWord<LbT>::VALID)) {
+				if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); break; }
+				w = ld_relaxed(p);
+			}
+			if (prof_on && d == 0) atomicAdd(prof + 8, (u64) spins);
+			st_relaxed(p, (LbT) 0);                                  /* consumed: reset */
+			goff_of(gslot)[d] = my_base[j] + (w & PPWord<LbT>::VAL) - (LbT) s_ds[dslot * RADIX + d];
 		}
-		if (prof_on && d == 0) atomicAdd(prof + 8, (u64) spins);
-		st_relaxed(p, (LbT) 0);                                  /* consumed: reset */
-		goff_of(gslot)[d] = my_base + (w & PPWord<LbT>::VAL) - (LbT) s_ds[dslot * RADIX + d];
 	};
 	auto repair = [&](u32 t, int b, int gslot, int dslot) {
 		v6_repair<ElemT, LbT, THREADS, IPT>(in, out, n, t, reinterpret_cast<u32*>(s_buf + (size_t) b * TILE),
@@ -262,10 +301,14 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	u32 t1 = NONE, t2 = NONE;         /* tiles of the previous two iterations (staged, not yet written) */
 	int b = 0;                        /* buffer of the current tile (= buffer of t2) */
 	int s0 = 0, s1 = 2, s2 = 1;       /* s_ds slots of cur, t1, t2 (k, k-1, k-2 mod 3) */
-	const bool is_pref_thread = tid >= RADIX && tid < 2 * RADIX;
+	const bool is_pref_thread = tid >= RADIX;
+	const LbT zero_w[DPT] = {};
 	for (;;) {
-		LbT wp = 0;
-		if (t2 != NONE && is_pref_thread) wp = ld_relaxed(pref + (size_t) t2 * RADIX + (tid - RADIX));
+		LbT wp[DPT] = {};
+		if (t2 != NONE && is_pref_thread) {
+#pragma unroll
+			for (int j = 0; j < DPT; ++j) wp[j] = ld_relaxed(pref + (size_t) t2 * RADIX + (tid - RADIX + j * PREF_T));
+		}
 		const u32 cnt = tile_count_of(cur);
 		/* P1 count */
 		if (cnt == (u32) TILE) {
@@ -358,7 +401,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		const int ss = r == 0 ? s2 : s1;
 		__syncthreads();
 		if (t == NONE) continue;
-		if (is_pref_thread) prefix_to_goff(t, 0, ss, (LbT) 0);
+		if (is_pref_thread) prefix_to_goff(t, 0, ss, zero_w);
 		__syncthreads();
 		const bool bad = write_out(t, bb, 0, true);
 		if (__syncthreads_or(bad ? 1 : 0)) repair(t, bb, 0, ss);
@@ -368,9 +411,12 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	int b = 0;
 	u32 it = 0;
 	for (;;) {
-		LbT wp = 0;
-		const bool is_pref_thread = tid >= RADIX && tid < 2 * RADIX;
-		if (prev != NONE && is_pref_thread) wp = ld_relaxed(pref + (size_t) prev * RADIX + (tid - RADIX));
+		LbT wp[DPT] = {};
+		const bool is_pref_thread = tid >= RADIX;
+		if (prev != NONE && is_pref_thread) {
+#pragma unroll
+			for (int j = 0; j < DPT; ++j) wp[j] = ld_relaxed(pref + (size_t) prev * RADIX + (tid - RADIX + j * PREF_T));
+		}
 		const u32 cnt = tile_count_of(cur);
 		/* P1 count */
 		if (cnt == (u32) TILE) {
@@ -459,7 +505,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	/* ---- epilogue: `prev` is staged in buffer b^1; pprev was written in the last iteration */
 	__syncthreads();
 	if (s_misc[10 + ((it + 1) & 1)]) repair(pprev, b, b, b);
-	if (tid >= RADIX && tid < 2 * RADIX) prefix_to_goff(prev, b ^ 1, b ^ 1, (LbT) 0);
+	{ const LbT zw[DPT] = {}; if (tid >= RADIX) prefix_to_goff(prev, b ^ 1, b ^ 1, zw); }
 	__syncthreads();
 	const bool bad = write_out(prev, b ^ 1, b ^ 1, true);
 	if (__syncthreads_or(bad ? 1 : 0)) repair(prev, b ^ 1, b ^ 1, b ^ 1);
@@ -470,7 +516,7 @@ template <typename ElemT, int THREADS, int IPT, typename LbT>
 constexpr size_t onesweep_v6_smem() {
 	constexpr size_t worker = (size_t) (THREADS / 32) * RADIX * 4 + 4 * RADIX * 4 + 2 * RADIX * 8 + 16 * 4 +
 		2 * (size_t) THREADS * IPT * sizeof(ElemT);
-	constexpr size_t prop = pp_propagate2_smem<LbT, THREADS, V6_PROP_GROUPS>();
+	constexpr size_t prop = pp_propagate2_smem<LbT, THREADS, v6_prop_groups(THREADS)>();
 	return worker > prop ? worker : prop;
 }
 

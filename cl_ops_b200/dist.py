@@ -241,13 +241,23 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None,
     #    after the gather from the gathered counts, so nothing has to come back to the host.
     cap = samples_per_rank or 64 * P
     s = min(cap, n_local)
-    row = torch.zeros(2 + 2 * cap, dtype=torch.int64, device=dev)
-    row[0] = n_local
-    row[1] = s
-    if s > 0:
-        pos = (torch.arange(s, dtype=torch.int64, device=dev) * n_local) // s
-        row[2:2 + s] = _unsigned_order_i64(keys[pos], key_bits)
-        row[2 + cap:2 + cap + s] = pos
+    # the header and the sample positions only depend on (n_local, cap): built once
+    cache = getattr(ops, "_sample_cache", None)
+    if cache is None:
+        cache = {}
+        try:
+            ops._sample_cache = cache
+        except Exception:
+            pass
+    ck = (n_local, cap, str(dev))
+    if ck not in cache:
+        pos = (torch.arange(s, dtype=torch.int64, device=dev) * n_local) // max(s, 1)
+        pad = torch.zeros(cap - s, dtype=torch.int64, device=dev)
+        cache[ck] = (torch.tensor([n_local, s], dtype=torch.int64, device=dev), pos, pad,
+                     torch.arange(cap, dtype=torch.int64, device=dev)[None, :],
+                     torch.arange(1, P, dtype=torch.int64, device=dev))
+    hdr, pos, pad, lane_idx, pick_mul = cache[ck]
+    row = torch.cat([hdr, _unsigned_order_i64(keys[pos], key_bits), pad, pos, pad])
     allr = torch.empty(P * (2 + 2 * cap), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(allr, row, group=group)
     allr = allr.view(P, 2 + 2 * cap)
@@ -261,12 +271,12 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None,
     #    The gathered samples are already in global-index order (rank, then position), so ONE
     #    stable sort by key gives the lexicographic (key, index) order; unused slots carry the
     #    largest key and sort behind everything.  All on the device: no host round trip.
-    valid = torch.arange(cap, dtype=torch.int64, device=dev)[None, :] < allr[:, 1:2]
+    valid = lane_idx < allr[:, 1:2]
     all_k = torch.where(valid, allr[:, 2:2 + cap], _I64_MAX).reshape(-1)
     all_i = (allr[:, 2 + cap:] + g0_all[:, None]).reshape(-1)
     order = torch.argsort(all_k, stable=True)
     total = allr[:, 1].sum()
-    pick = (torch.arange(1, P, dtype=torch.int64, device=dev) * total) // P
+    pick = (pick_mul * total) // P
     sel = order[pick]
     spl_k64, spl_i = all_k[sel], all_i[sel]
     if key_bits == 32:
