@@ -39,6 +39,23 @@ typedef uint16_t cl_half;
 typedef float cl_float;
 typedef double cl_double;
 typedef cl_uint cl_bool;
+/* limits of the OpenCL scalar types (CL/cl_platform.h), used by src/benchmarks/clo_bench.c:33-142 */
+#define CL_CHAR_MAX 127
+#define CL_CHAR_MIN (-127 - 1)
+#define CL_UCHAR_MAX 255
+#define CL_SHRT_MAX 32767
+#define CL_SHRT_MIN (-32767 - 1)
+#define CL_USHRT_MAX 65535
+#define CL_INT_MAX 2147483647
+#define CL_INT_MIN (-2147483647 - 1)
+#define CL_UINT_MAX 0xffffffffU
+#define CL_LONG_MAX ((cl_long) 0x7FFFFFFFFFFFFFFFLL)
+#define CL_LONG_MIN ((cl_long) -0x7FFFFFFFFFFFFFFFLL - 1LL)
+#define CL_ULONG_MAX ((cl_ulong) 0xFFFFFFFFFFFFFFFFULL)
+#define CL_FLT_MAX 340282346638528859811704183484516925440.0f
+#define CL_FLT_MIN 1.175494350822287507969e-38f
+#define CL_DBL_MAX 1.7976931348623157e308
+#define CL_DBL_MIN 2.225073858507201383090e-308
 typedef cl_ulong cl_mem_flags;
 typedef cl_ulong cl_command_queue_properties;
 

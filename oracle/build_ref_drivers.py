@@ -1,0 +1,46 @@
+"""oracle/build_ref_drivers.py -- compile the reference's OWN benchmark drivers, unchanged, from
+where they lie under /root/reference (src/benchmarks/clo_sort_bench.c, clo_scan_bench.c,
+clo_bench.c; the error macros of src/cl_ops/common/_g_err_macros.h) against this repository's
+headers (include/, include/compat/{glib,cf4ocl2}.h) and link them with cl_ops_b200/libcl_ops.so.
+
+Outputs go to oracle/_ref/ only (git-ignored binaries; no reference source is copied).  This is
+the "existing src/benchmarks drivers relink unchanged" check of BASELINE.json's north_star:
+the drivers verify their own results (sorted order, clo_sort_bench.c:216-226; scan == serial
+host scan, clo_scan_bench.c:253-270), so running them on the GPU box is a parity test written
+by the reference's author.  Not built: clo_rng_bench / test_rng (they compile an OpenCL kernel
+string through ccl_program_*, which has no CUDA meaning without NVRTC).
+"""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "oracle", "_ref")
+
+
+def main():
+    bench = os.path.join(REF, "src", "benchmarks")
+    if not os.path.isdir(bench):
+        print("build_ref_drivers: %s not present, nothing built" % bench)
+        return 0
+    os.makedirs(OUT, exist_ok=True)
+    inc = ["-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "include", "compat"),
+           "-I" + bench, "-I" + os.path.join(REF, "src", "cl_ops")]
+    objs = {}
+    for name in ("clo_bench", "clo_sort_bench", "clo_scan_bench"):
+        o = os.path.join(OUT, name + ".o")
+        subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-w"] + inc + ["-c", os.path.join(bench, name + ".c"), "-o", o])
+        objs[name] = o
+    for exe in ("clo_sort_bench", "clo_scan_bench"):
+        subprocess.check_call(["gcc", "-o", os.path.join(OUT, exe), objs[exe], objs["clo_bench"],
+                               "-L" + os.path.join(ROOT, "cl_ops_b200"), "-lcl_ops", "-lm",
+                               "-Wl,-rpath,$ORIGIN/../../cl_ops_b200"])
+    for o in objs.values():
+        os.remove(o)
+    print("build_ref_drivers: wrote %s/{clo_sort_bench,clo_scan_bench}" % OUT)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
