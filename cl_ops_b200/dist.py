@@ -20,6 +20,8 @@ The local operators are injected (`ops`), so the host-side logic can be exercise
 gloo on CPU tensors by the tests; the product binding is `GpuOps`, which calls the C-ABI
 library and has no fallback.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -212,6 +214,58 @@ def _exchange(src, dst, send_list, recv_list, r, P, group):
         w.wait()
 
 
+class _Graphed:
+    """A pure device function of STATIC input tensors, captured once as a CUDA graph and
+    replayed: the dozen small kernels of the splitter selection (and of the bucket-size
+    bookkeeping) cost one launch instead of twelve.  Plumbing only."""
+
+    def __init__(self, fn, inputs):
+        self.inputs = inputs
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fn(*inputs)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.outputs = fn(*inputs)
+
+    def __call__(self):
+        self.graph.replay()
+        return self.outputs
+
+
+def _pick_splitters(allr, lane_idx, pick_mul, P, cap, key_bits):
+    """P-1 splitters (key, global index) from the gathered sample rows; device only."""
+    n_all = allr[:, 0]
+    g0_all = torch.cumsum(n_all, 0) - n_all
+    valid = lane_idx < allr[:, 1:2]
+    all_k = torch.where(valid, allr[:, 2:2 + cap], _I64_MAX).reshape(-1)
+    all_i = (allr[:, 2 + cap:] + g0_all[:, None]).reshape(-1)
+    order = torch.argsort(all_k, stable=True)
+    total = allr[:, 1].sum()
+    pick = (pick_mul * total) // P
+    sel = order[pick]
+    spl_k64, spl_i = all_k[sel], all_i[sel]
+    if key_bits == 32:
+        spl_keys = spl_k64.to(torch.int32)            # low 32 bits = the raw u32 pattern
+    else:
+        spl_keys = spl_k64 ^ _SIGN64
+    return spl_keys.contiguous(), spl_i.contiguous(), g0_all
+
+
+def _slots_from_sizes(M, r, P, capacity):
+    """M[src][dst] bucket sizes -> (first slot of my bucket in every destination, fits flag,
+    [what I receive from each source, what I send to each destination, fits])"""
+    first_slot = torch.zeros(16, dtype=torch.int64, device=M.device)
+    first_slot[:P] = (torch.cumsum(M, 0) - M)[r]
+    ok = (M.sum(0) <= capacity).all().to(torch.int32).reshape(1)
+    host = torch.cat([M[:, r], M[r], ok.to(torch.int64)])
+    return first_slot, ok, host
+
+
 def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None, profile=False, gidx0=None):
     """Globally stable sort of the concatenation of every rank's `keys` (rank order).
 
@@ -258,32 +312,29 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None,
                      torch.arange(1, P, dtype=torch.int64, device=dev))
     hdr, pos, pad, lane_idx, pick_mul = cache[ck]
     row = torch.cat([hdr, _unsigned_order_i64(keys[pos], key_bits), pad, pos, pad])
-    allr = torch.empty(P * (2 + 2 * cap), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(allr, row, group=group)
-    allr = allr.view(P, 2 + 2 * cap)
-    n_all = allr[:, 0]
-    g0_all = torch.cumsum(n_all, 0) - n_all
-    if gidx0 is None:
-        gidx0 = int(g0_all[r].item())
+    use_graphs = keys.is_cuda and os.environ.get("CLO_DIST_GRAPHS", "1") != "0"
+    gk = ("spl", P, cap, key_bits, str(dev))
+    if use_graphs and gk in cache:
+        allr, spl_graph = cache[gk]
+    else:
+        allr = torch.empty(P, 2 + 2 * cap, dtype=torch.int64, device=dev)
+        spl_graph = None
+    dist.all_gather_into_tensor(allr.view(-1), row, group=group)
     ph.mark("samples+allgather")
 
     # 2) splitters (identical on every rank: same data, same deterministic procedure).
     #    The gathered samples are already in global-index order (rank, then position), so ONE
     #    stable sort by key gives the lexicographic (key, index) order; unused slots carry the
     #    largest key and sort behind everything.  All on the device: no host round trip.
-    valid = lane_idx < allr[:, 1:2]
-    all_k = torch.where(valid, allr[:, 2:2 + cap], _I64_MAX).reshape(-1)
-    all_i = (allr[:, 2 + cap:] + g0_all[:, None]).reshape(-1)
-    order = torch.argsort(all_k, stable=True)
-    total = allr[:, 1].sum()
-    pick = (pick_mul * total) // P
-    sel = order[pick]
-    spl_k64, spl_i = all_k[sel], all_i[sel]
-    if key_bits == 32:
-        spl_keys = spl_k64.to(torch.int32)            # low 32 bits = the raw u32 pattern
+    if use_graphs:
+        if spl_graph is None:
+            spl_graph = _Graphed(lambda a: _pick_splitters(a, lane_idx, pick_mul, P, cap, key_bits), [allr])
+            cache[gk] = (allr, spl_graph)
+        spl_keys, spl_i, g0_all = spl_graph()
     else:
-        spl_keys = spl_k64 ^ _SIGN64
-    spl_keys, spl_i = spl_keys.contiguous(), spl_i.contiguous()
+        spl_keys, spl_i, g0_all = _pick_splitters(allr, lane_idx, pick_mul, P, cap, key_bits)
+    if gidx0 is None:
+        gidx0 = int(g0_all[r].item())
     ph.mark("splitters")
 
     # 3+4 fused) count -> all-gather of the P x P bucket sizes -> every bucket is scattered
@@ -292,19 +343,25 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None,
     if pe is not None and pe["with_payload"] == (payload is not None):
         counts = ops.partition_count(keys, gidx0, spl_keys, spl_i, P)
         ph.mark("count")
-        M = torch.empty(P * P, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(M, counts, group=group)
-        M = M.view(P, P)                                   # M[src][dst]
-        first_slot = torch.zeros(16, dtype=torch.int64, device=dev)
-        first_slot[:P] = (torch.cumsum(M, 0) - M)[r]
-        col = M.sum(0)
-        ok = (col <= pe["capacity"]).all().to(torch.int32).reshape(1)
+        mk = ("sizes", P, r, pe["capacity"], str(dev))
+        if use_graphs and mk in cache:
+            M, size_graph = cache[mk]
+        else:
+            M, size_graph = torch.empty(P, P, dtype=torch.int64, device=dev), None
+        dist.all_gather_into_tensor(M.view(-1), counts, group=group)        # M[src][dst]
+        if use_graphs:
+            if size_graph is None:
+                size_graph = _Graphed(lambda m: _slots_from_sizes(m, r, P, pe["capacity"]), [M])
+                cache[mk] = (M, size_graph)
+            first_slot, ok, host_vec = size_graph()
+        else:
+            first_slot, ok, host_vec = _slots_from_sizes(M, r, P, pe["capacity"])
         ph.mark("sizes all-gather")
         ops.partition_scatter(keys, payload, gidx0, spl_keys, spl_i, P, first_slot, ok)
         ph.mark("scatter to peers")
         done = torch.zeros(1, dtype=torch.int32, device=dev)
         dist.all_reduce(done, group=group)                 # every peer's writes have landed
-        host = torch.cat([M[:, r], M[r], ok.to(torch.int64)]).tolist()   # the one host synchronisation
+        host = host_vec.tolist()                           # the one host synchronisation
         recv_list, send_list, fits = host[:P], host[P:2 * P], bool(host[2 * P])
         ph.mark("barrier+sizes to host")
         if fits:
