@@ -503,7 +503,7 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 template <typename ElemT, bool HAS_VAL> struct TileCfg {
 	/* keys-only: 512 x 16 (4 B and narrower), 512 x 8 (8 B); with payload: 512 x 12 / 512 x 8 */
 	static const int THREADS = 512;
-	static const int IPT = HAS_VAL ? (sizeof(ElemT) == 8 ? 8 : 12) : (sizeof(ElemT) == 8 ? 8 : 16);
+	static const int IPT = HAS_VAL ? (sizeof(ElemT) == 8 ? 6 : 8) : (sizeof(ElemT) == 8 ? 8 : 16);
 };
 
 template <typename ElemT, bool HAS_VAL, int THREADS, int IPT, bool USE_INFO = true>
@@ -522,6 +522,7 @@ struct CloRadixState {
 	CloScratch pp;           /* AGG + PREF words of the persistent kernel (self-cleaning) */
 	int kernel_pp = 1;       /* CLO_RADIX_KERNEL=classic selects the one-tile-per-CTA kernel */
 	int kernel_v6 = 1;       /* keys-only sorts use the two-barrier kernel; CLO_RADIX_KERNEL=pp|classic turn it off */
+	int force_wide = 0;      /* CLO_RADIX_WIDE=1: 64-bit look-back words whatever n is (test hook for the >= 2^31 path) */
 	int rank_atomic = 1;     /* CLO_RADIX_RANK=ballot selects the ballot ranks */
 	int cfg = 0;
 	/* optional per-kernel timing of the last call (clo_radix_set_timing) */
@@ -546,6 +547,8 @@ CloRadixState* clo_radix_state_new() {
 	g_pp_flags = (ppf && *ppf) ? atoi(ppf) : 0;
 	const char* pf = getenv("CLO_RADIX_PROFILE");
 	g_radix_profile = (pf && *pf == '1') ? 1 : 0;
+	const char* fw = getenv("CLO_RADIX_WIDE");
+	st->force_wide = (fw && *fw == '1') ? 1 : 0;
 	const char* c = getenv("CLO_RADIX_CFG");
 	st->cfg = (c && *c) ? atoi(c) : 0;
 	return st;
@@ -708,8 +711,10 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		cfg.dmask[p] = (1u << (rem < (u32) RADIX_BITS ? rem : (u32) RADIX_BITS)) - 1;
 	}
 	const size_t tiles = (n + TILE - 1) / TILE;
-	const bool wide = n >= (1ull << 30);
 	const bool use_pp = st->kernel_pp != 0;
+	/* look-back words: the classic kernel keeps 30 value bits, the persistent ones 31 (every
+	 * prefix and offset is a count of keys, i.e. < n) */
+	const bool wide = st->force_wide || n >= (use_pp ? (1ull << 31) : (1ull << 30));
 	WorkLayout L;
 	if ((e = prepare_work(st, use_pp ? 0 : tiles, cfg.passes, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
 	if (use_pp) {
@@ -755,11 +760,11 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		u32* vnxt = to_dst ? vdst : vaux;
 		u32* ticket = L.tickets + p;
 		bool done_v6 = false;
-		if constexpr (!HAS_VAL && IDENTITY && sizeof(ElemT) >= 4 && THREADS > RADIX) {
+		if constexpr (IDENTITY && sizeof(ElemT) >= 4 && THREADS > RADIX) {
 			if (use_pp && st->kernel_v6) {
 				char* agg = (char*) st->pp.ptr;
 				char* pref = agg + tiles * RADIX * (wide ? 8 : 4);
-				e = clo_radix_v6_pass((int) sizeof(ElemT), wide ? 1 : 0, THREADS * IPT, cur, nxt, n, agg, pref, ticket,
+				e = clo_radix_v6_pass((int) sizeof(ElemT), wide ? 1 : 0, THREADS * IPT, cur, nxt, HAS_VAL ? vcur : nullptr, HAS_VAL ? vnxt : nullptr, n, agg, pref, ticket,
 					L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], L.err, sm_count, g_radix_profile, g_pp_flags, stream);
 				done_v6 = true;
 			}

@@ -171,7 +171,7 @@ __device__ __forceinline__ void pp_propagate2(LbT* __restrict__ agg, LbT* __rest
 		int* __restrict__ err_flag, unsigned char* smem_raw, int prof_on, int cta_index) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int WPG = WARPS / G;                 /* warps per group */
-	constexpr int C = PP2_CHUNK;                   /* tiles per warp and round */
+	constexpr int C = sizeof(LbT) == 8 ? PP2_CHUNK / 2 : PP2_CHUNK;   /* tiles per warp and round (64-bit words: half, to stay in registers) */
 	static_assert(WARPS % G == 0, "bad propagator shape");
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int grp = warp / WPG, wg = warp % WPG;

@@ -14,12 +14,12 @@ namespace {
 #include "radix_prop.cuh"
 #include "radix_v6.cuh"
 
-template <typename ElemT, typename LbT, int THREADS, int IPT, int ABL = 0>
-cudaError_t launch_v6(int tile, const ElemT* in, ElemT* out, size_t n, LbT* agg, LbT* pref, u32* ticket,
+template <typename ElemT, typename LbT, int THREADS, int IPT, bool HAS_VAL>
+cudaError_t launch_v6(int tile, const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n, LbT* agg, LbT* pref, u32* ticket,
 		const u64* bins, u32 start_bit, u32 dmask, int* err, int sm_count, int prof_on, int flags, cudaStream_t stream) {
 	if (tile != THREADS * IPT) return cudaErrorInvalidValue;
-	constexpr size_t SMEM = onesweep_v6_smem<ElemT, THREADS, IPT, LbT>();
-	auto kern = clo_radix_onesweep_v6<ElemT, LbT, THREADS, IPT, ABL>;
+	constexpr size_t SMEM = onesweep_v6_smem<ElemT, THREADS, IPT, LbT, HAS_VAL>();
+	auto kern = clo_radix_onesweep_v6<ElemT, LbT, THREADS, IPT, HAS_VAL>;
 	static bool configured[64] = {};
 	static int ctas_per_sm[64] = {};
 	int dev = 0;
@@ -35,36 +35,28 @@ cudaError_t launch_v6(int tile, const ElemT* in, ElemT* out, size_t n, LbT* agg,
 	}
 	const size_t tiles = (n + (size_t) tile - 1) / (size_t) tile;
 	size_t workers = (size_t) sm_count * ctas_per_sm[dev];
-	constexpr int V6_NUM_PROP = v6_num_prop(THREADS);
+	constexpr int V6_NUM_PROP = v6_num_prop(THREADS, (int) sizeof(LbT));
 	workers = workers > (size_t) V6_NUM_PROP ? workers - V6_NUM_PROP : 1;
 	if (workers > tiles) workers = tiles;
-	kern<<<(unsigned) (V6_NUM_PROP + workers), THREADS, SMEM, stream>>>(in, out, n, (u32) tiles,
+	kern<<<(unsigned) (V6_NUM_PROP + workers), THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u32) tiles,
 		agg, pref, ticket, bins, start_bit, dmask, err, prof_on, flags);
 	CLO_COUNT_LAUNCH(1);
 	return cudaGetLastError();
 }
 } // namespace
 
-cudaError_t clo_radix_v6_pass(int elem_size, int wide, int tile, const void* in, void* out, size_t n,
+/* tile sizes: keys only 512 x 16 (4-byte keys) / 512 x 8 (8-byte keys); with a u32 payload
+ * 512 x 8 / 512 x 6, so that two CTAs and their double staging buffers fit one SM */
+cudaError_t clo_radix_v6_pass(int elem_size, int wide, int tile, const void* in, void* out,
+		const uint32_t* vin, uint32_t* vout, size_t n,
 		void* agg, void* pref, uint32_t* ticket, const unsigned long long* bins, uint32_t start_bit,
 		uint32_t dmask, int* err, int sm_count, int prof_on, int flags, cudaStream_t stream) {
-#ifdef CLO_V6_ABLATION
-	if (elem_size == 4 && !wide && (flags >> 8)) {
-		switch (flags >> 8) {
-		case 1: return launch_v6<u32, u32, 512, 16, 1>(tile, (const u32*) in, (u32*) out, n, (u32*) agg, (u32*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-		case 2: return launch_v6<u32, u32, 512, 16, 2>(tile, (const u32*) in, (u32*) out, n, (u32*) agg, (u32*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-		case 3: return launch_v6<u32, u32, 512, 16, 3>(tile, (const u32*) in, (u32*) out, n, (u32*) agg, (u32*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-		case 4: return launch_v6<u32, u32, 512, 16, 4>(tile, (const u32*) in, (u32*) out, n, (u32*) agg, (u32*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-		}
-	}
-#endif
-	if (elem_size == 4) {
-		if (wide) return launch_v6<u32, u64, 512, 16>(tile, (const u32*) in, (u32*) out, n, (u64*) agg, (u64*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-		return launch_v6<u32, u32, 512, 16>(tile, (const u32*) in, (u32*) out, n, (u32*) agg, (u32*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-	}
-	if (elem_size == 8) {
-		if (wide) return launch_v6<u64, u64, 512, 8>(tile, (const u64*) in, (u64*) out, n, (u64*) agg, (u64*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-		return launch_v6<u64, u32, 512, 8>(tile, (const u64*) in, (u64*) out, n, (u32*) agg, (u32*) pref, ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream);
-	}
+#define CLO_V6_GO(ET, LT, IPT_, HV) launch_v6<ET, LT, 512, IPT_, HV>(tile, (const ET*) in, (ET*) out, vin, vout, n, (LT*) agg, (LT*) pref, \
+		ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream)
+	if (elem_size == 4 && !vin) return wide ? CLO_V6_GO(u32, u64, 16, false) : CLO_V6_GO(u32, u32, 16, false);
+	if (elem_size == 8 && !vin) return wide ? CLO_V6_GO(u64, u64, 8, false) : CLO_V6_GO(u64, u32, 8, false);
+	if (elem_size == 4 && vin) return wide ? CLO_V6_GO(u32, u64, 8, true) : CLO_V6_GO(u32, u32, 8, true);
+	if (elem_size == 8 && vin) return wide ? CLO_V6_GO(u64, u64, 6, true) : CLO_V6_GO(u64, u32, 6, true);
+#undef CLO_V6_GO
 	return cudaErrorInvalidValue;
 }

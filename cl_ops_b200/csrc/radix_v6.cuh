@@ -44,8 +44,9 @@ __device__ __forceinline__ u32 v6_digit(ElemT k, u32 start_bit, u32 dmask) {
  * written out in a wrong intra-digit order) is ranked again with ballots and scattered
  * straight to its final positions.  scratch is the tile's own staging buffer ([WARPS][RADIX]
  * words are used); goff and ds are still those of tile t.  Called by all threads of the CTA. */
-template <typename ElemT, typename LbT, int THREADS, int IPT>
-__device__ __noinline__ void v6_repair(const ElemT* __restrict__ in, ElemT* __restrict__ out, size_t n, u32 t,
+template <typename ElemT, typename LbT, int THREADS, int IPT, bool HAS_VAL>
+__device__ __noinline__ void v6_repair(const ElemT* __restrict__ in, ElemT* __restrict__ out,
+		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n, u32 t,
 		u32* scratch, const LbT* goff, const u32* ds, u32 start_bit, u32 dmask, int* err_flag) {
 	constexpr int WARPS = THREADS / 32;
 	constexpr int TILE = THREADS * IPT;
@@ -58,6 +59,7 @@ __device__ __noinline__ void v6_repair(const ElemT* __restrict__ in, ElemT* __re
 	__syncthreads();
 	u32* sw = scratch + warp * RADIX;
 	ElemT key[IPT];
+	u32 val[HAS_VAL ? IPT : 1];
 	u32 rank[IPT];
 #pragma unroll 1
 	for (int i = 0; i < IPT; ++i) {
@@ -85,19 +87,22 @@ __device__ __noinline__ void v6_repair(const ElemT* __restrict__ in, ElemT* __re
 		const u32 local = wbase + i * 32u;
 		if (local < cnt) {
 			const u32 d = v6_digit<ElemT>(key[i], start_bit, dmask);
-			out[goff[d] + (LbT) (ds[d] + sw[d] + rank[i])] = key[i];
+			const LbT o = goff[d] + (LbT) (ds[d] + sw[d] + rank[i]);
+			out[o] = key[i];
+			if (HAS_VAL) vout[o] = vin[base + local];
 		}
 	}
 	__syncthreads();
 }
 
 /* propagator groups (32 digits each) per CTA and propagator CTAs, by CTA size */
-__host__ __device__ constexpr int v6_prop_groups(int threads) { return threads >= 512 ? 2 : 1; }
-__host__ __device__ constexpr int v6_num_prop(int threads) { return RADIX / 32 / v6_prop_groups(threads); }
+__host__ __device__ constexpr int v6_prop_groups(int threads, int word_bytes) { return (threads >= 512 && word_bytes == 4) ? 2 : 1; }
+__host__ __device__ constexpr int v6_num_prop(int threads, int word_bytes) { return RADIX / 32 / v6_prop_groups(threads, word_bytes); }
 
-template <typename ElemT, typename LbT, int THREADS, int IPT, int ABL = 0, bool DEEP = true>
+template <typename ElemT, typename LbT, int THREADS, int IPT, bool HAS_VAL = false>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 3 : 2))
-clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, size_t n, u32 num_tiles,
+clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
+		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n, u32 num_tiles,
 		LbT* __restrict__ agg, LbT* __restrict__ pref, u32* __restrict__ ticket,
 		const u64* __restrict__ bins_base, u32 start_bit, u32 dmask,
 		int* __restrict__ err_flag, int prof_on, int flags) {
@@ -108,6 +113,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	constexpr int PREF_T = THREADS - RADIX;        /* prefix threads */
 	constexpr int DPT = RADIX / PREF_T;            /* digits per prefix thread */
 	static_assert((size_t) TILE * sizeof(ElemT) >= (size_t) WARPS * RADIX * 4, "repair scratch lives in a staging buffer");
+	static_assert(TILE <= 65536, "index in tile must fit 16 bits");
 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -124,7 +130,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		}
 		__syncthreads();
 		if (s_trivial) {
-			constexpr int NP = v6_num_prop(THREADS);
+			constexpr int NP = v6_num_prop(THREADS, (int) sizeof(LbT));
 			if (blockIdx.x < NP) return;
 			const u32 wb = (u32) (threadIdx.x >> 5) * 32u * IPT + (threadIdx.x & 31);
 			for (u32 t = blockIdx.x - NP; t < num_tiles; t += gridDim.x - NP) {
@@ -132,7 +138,10 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 #pragma unroll
 				for (int i = 0; i < IPT; ++i) {
 					const size_t j = base + wb + i * 32u;
-					if (j < n) out[j] = __ldcs(in + j);
+					if (j < n) {
+						out[j] = __ldcs(in + j);
+						if (HAS_VAL) vout[j] = __ldcs(vin + j);
+					}
 				}
 			}
 			return;
@@ -145,8 +154,8 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	u32* prop_sm = reinterpret_cast<u32*>(err_flag + 48);       /* [PP_NUM_PROP], zeroed per call */
 	u32 my_sm;
 	asm volatile("mov.u32 %0, %%smid;" : "=r"(my_sm));
-	constexpr int V6_PROP_GROUPS = v6_prop_groups(THREADS);
-	constexpr int V6_NUM_PROP = v6_num_prop(THREADS);
+	constexpr int V6_PROP_GROUPS = v6_prop_groups(THREADS, (int) sizeof(LbT));
+	constexpr int V6_NUM_PROP = v6_num_prop(THREADS, (int) sizeof(LbT));
 	if (blockIdx.x < V6_NUM_PROP) {
 		if (threadIdx.x == 0) st_relaxed(prop_sm + blockIdx.x, my_sm + 1u);
 		pp_propagate2<LbT, THREADS, V6_PROP_GROUPS>(agg, pref, num_tiles, err_flag, smem_raw, prof_on, (int) blockIdx.x);
@@ -172,7 +181,13 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	u32* s_ds = whist + WARPS * RADIX;                                      /* [2][RADIX] digit starts */
 	u64* s_goff_raw = reinterpret_cast<u64*>(s_ds + 4 * RADIX);             /* [2][RADIX] u64-sized slots (s_ds has 3 live slots + 1 pad) */
 	u32* s_misc = reinterpret_cast<u32*>(s_goff_raw + 2 * RADIX);           /* [16]: 0..7 scan, 8 ticket, 10..11 bad */
-	ElemT* s_buf = reinterpret_cast<ElemT*>(s_misc + 16);                   /* [2][TILE] */
+	/* staging, per buffer: keys [TILE]; with a payload also values [TILE] and the index in tile
+	 * of every staged element [TILE] (u16), which is what the stability check compares */
+	constexpr size_t BUF_BYTES = (size_t) TILE * sizeof(ElemT) + (HAS_VAL ? (size_t) TILE * 6 : 0);
+	unsigned char* s_buf_raw = reinterpret_cast<unsigned char*>(s_misc + 16);   /* [2][BUF_BYTES] */
+	auto buf_keys = [&](int b) { return reinterpret_cast<ElemT*>(s_buf_raw + (size_t) b * BUF_BYTES); };
+	auto buf_vals = [&](int b) { return reinterpret_cast<u32*>(s_buf_raw + (size_t) b * BUF_BYTES + (size_t) TILE * sizeof(ElemT)); };
+	auto buf_info = [&](int b) { return reinterpret_cast<unsigned short*>(s_buf_raw + (size_t) b * BUF_BYTES + (size_t) TILE * (sizeof(ElemT) + 4)); };
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const ElemT low_mask = (ElemT) ((((ElemT) dmask) << start_bit) | ((((ElemT) 1) << start_bit) - 1));
@@ -184,6 +199,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	for (int j = 0; j < DPT; ++j) my_base[j] = tid >= RADIX ? (LbT) bins_base[tid - RADIX + j * PREF_T] : (LbT) 0;
 
 	ElemT key[IPT];
+	u32 val[HAS_VAL ? IPT : 1];
 
 	/* optional phase profile: cycles per phase, thread 0 (digit side) and thread 256 (prefix side) */
 	u64* prof = reinterpret_cast<u64*>(err_flag + 16);
@@ -206,12 +222,20 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		const size_t base = (size_t) t * TILE;
 		const u32 cnt = tile_count_of(t);
 		const ElemT* p = in + base + wbase;
+		const u32* pv = vin + base + wbase;
 		if (cnt == (u32) TILE) {
 #pragma unroll
-			for (int i = 0; i < IPT; ++i) key[i] = __ldcs(p + i * 32);
+			for (int i = 0; i < IPT; ++i) {
+				key[i] = __ldcs(p + i * 32);
+				if (HAS_VAL) val[i] = __ldcs(pv + i * 32);
+			}
 		} else {
 #pragma unroll
-			for (int i = 0; i < IPT; ++i) key[i] = (wbase + i * 32u < cnt) ? __ldcs(p + i * 32) : ElemT(0);
+			for (int i = 0; i < IPT; ++i) {
+				const bool in_tile = wbase + i * 32u < cnt;
+				key[i] = in_tile ? __ldcs(p + i * 32) : ElemT(0);
+				if (HAS_VAL) val[i] = in_tile ? __ldcs(pv + i * 32) : 0u;
+			}
 		}
 	};
 	auto zero_row = [&]() {
@@ -224,7 +248,9 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	 * applied in lane order) */
 	auto write_out = [&](u32 t, int b, int gslot, bool verify) -> bool {
 		const u32 cnt = tile_count_of(t);
-		const ElemT* skeys = s_buf + (size_t) b * TILE;
+		const ElemT* skeys = buf_keys(b);
+		const u32* svals = buf_vals(b);
+		const unsigned short* sinfo = buf_info(b);
 		const LbT* goff = goff_of(gslot);
 		bool bad = false;
 		if ((flags & 8) && (t % 5u) == 2u) {
@@ -232,32 +258,34 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 			 * path gives a sorted result */
 			for (u32 j = tid; j < cnt; j += THREADS) {
 				const ElemT k = skeys[j];
-				out[goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j] = (ElemT) ~k;
+				const LbT o = goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j;
+				out[o] = (ElemT) ~k;
+				if (HAS_VAL) vout[o] = ~svals[j];
 			}
 			return true;
 		}
+		auto one = [&](u32 j) {
+			const ElemT k = skeys[j];
+			const ElemT kp = skeys[j > 0 ? j - 1 : 0];
+			const u32 d = v6_digit<ElemT>(k, start_bit, dmask);
+			if (HAS_VAL) {
+				/* equal digits must keep their order in the tile (payloads tell equal keys apart) */
+				if (j > 0 && v6_digit<ElemT>(kp, start_bit, dmask) == d && sinfo[j] <= sinfo[j - 1]) bad = true;
+			} else {
+				if ((k & low_mask) < (kp & low_mask)) bad = true;
+			}
+			const LbT o = goff[d] + (LbT) j;
+			out[o] = k;
+			if (HAS_VAL) vout[o] = svals[j];
+		};
 		if (cnt == (u32) TILE) {
 #pragma unroll
-			for (int i = 0; i < IPT; ++i) {
-				const u32 j = (u32) tid + i * THREADS;
-				const ElemT k = skeys[j];
-				if (ABL != 1) {
-					const ElemT kp = skeys[j > 0 ? j - 1 : 0];
-					if ((k & low_mask) < (kp & low_mask)) bad = true;
-				}
-				const LbT o = goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j;
-				if (ABL != 2 || o == (LbT) ~(LbT) 0) out[o] = k;
-			}
+			for (int i = 0; i < IPT; ++i) one((u32) tid + i * THREADS);
 		} else {
 #pragma unroll
 			for (int i = 0; i < IPT; ++i) {
 				const u32 j = (u32) tid + i * THREADS;
-				if (j < cnt) {
-					const ElemT k = skeys[j];
-					const ElemT kp = skeys[j > 0 ? j - 1 : 0];
-					if ((k & low_mask) < (kp & low_mask)) bad = true;
-					out[goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j] = k;
-				}
+				if (j < cnt) one(j);
 			}
 		}
 		return verify && bad;
@@ -280,7 +308,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		}
 	};
 	auto repair = [&](u32 t, int b, int gslot, int dslot) {
-		v6_repair<ElemT, LbT, THREADS, IPT>(in, out, n, t, reinterpret_cast<u32*>(s_buf + (size_t) b * TILE),
+		v6_repair<ElemT, LbT, THREADS, IPT, HAS_VAL>(in, out, vin, vout, n, t, reinterpret_cast<u32*>(buf_keys(b)),
 			goff_of(gslot), s_ds + dslot * RADIX, start_bit, dmask, err_flag);
 	};
 
@@ -291,7 +319,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 	u32 cur = s_misc[8];
 	if (cur >= num_tiles) return;
 	load_tile(cur);
-	if constexpr (DEEP) {
+	{
 	/* ---- schedule with TWO iterations of slack between a tile's AGG and the use of its PREF:
 	 *   P1 count(k) | B1 | P2 digits(k) + PREF(k-2) -> offsets | B2 | write-out(k-2) | B3 |
 	 *   place(k) into the buffer just freed | load(k+1)
@@ -357,6 +385,11 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 			const size_t lo = (size_t) nxt * TILE * sizeof(ElemT) + (size_t) tid * 128;
 			if (lo < n * sizeof(ElemT) && (size_t) tid * 128 < (size_t) TILE * sizeof(ElemT))
 				asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(in) + lo));
+			if (HAS_VAL) {
+				const size_t lv = (size_t) nxt * TILE * 4 + (size_t) tid * 128;
+				if (lv < n * 4 && (size_t) tid * 128 < (size_t) TILE * 4)
+					asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(vin) + lv));
+			}
 		}
 		/* P5 write-out of the tile staged two iterations ago (same buffer as the current tile) */
 		bool bad = false;
@@ -366,22 +399,37 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		mark(5);
 		/* P3 place + P4 next tile: a key register is refilled as soon as its key is staged */
 		{
-			ElemT* skeys = s_buf + (size_t) b * TILE;
+			ElemT* skeys = buf_keys(b);
+			u32* svals = buf_vals(b);
+			unsigned short* sinfo = buf_info(b);
 			const bool next_full = more && tile_count_of(nxt) == (u32) TILE;
 			if (cnt == (u32) TILE && next_full) {
 				const ElemT* np = in + (size_t) nxt * TILE + wbase;
+				const u32* npv = vin + (size_t) nxt * TILE + wbase;
 #pragma unroll
 				for (int i = 0; i < IPT; ++i) {
-					skeys[atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u)] = key[i];
+					const u32 p = atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+					skeys[p] = key[i];
 					key[i] = __ldcs(np + i * 32);
+					if (HAS_VAL) {
+						svals[p] = val[i];
+						sinfo[p] = (unsigned short) (wbase + i * 32u);
+						val[i] = __ldcs(npv + i * 32);
+					}
 				}
 				__syncwarp();
 				zero_row();
 			} else {
 #pragma unroll
 				for (int i = 0; i < IPT; ++i)
-					if (wbase + i * 32u < cnt)
-						skeys[atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u)] = key[i];
+					if (wbase + i * 32u < cnt) {
+						const u32 p = atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+						skeys[p] = key[i];
+						if (HAS_VAL) {
+							svals[p] = val[i];
+							sinfo[p] = (unsigned short) (wbase + i * 32u);
+						}
+					}
 				__syncwarp();
 				zero_row();
 				if (more) load_tile(nxt);
@@ -406,117 +454,14 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out, siz
 		const bool bad = write_out(t, bb, 0, true);
 		if (__syncthreads_or(bad ? 1 : 0)) repair(t, bb, 0, ss);
 	}
-	} else {
-	u32 prev = NONE, pprev = NONE;
-	int b = 0;
-	u32 it = 0;
-	for (;;) {
-		LbT wp[DPT] = {};
-		const bool is_pref_thread = tid >= RADIX;
-		if (prev != NONE && is_pref_thread) {
-#pragma unroll
-			for (int j = 0; j < DPT; ++j) wp[j] = ld_relaxed(pref + (size_t) prev * RADIX + (tid - RADIX + j * PREF_T));
-		}
-		const u32 cnt = tile_count_of(cur);
-		/* P1 count */
-		if (cnt == (u32) TILE) {
-			if (ABL != 4) {
-#pragma unroll
-				for (int i = 0; i < IPT; ++i) atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
-			}
-		} else {
-#pragma unroll
-			for (int i = 0; i < IPT; ++i)
-				if (wbase + i * 32u < cnt) atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
-		}
-		mark(0);
-		__syncthreads();                                         /* B1 */
-		mark(1);
-		/* the write-out of the previous iteration (tile pprev, buffer b) reported a bad order */
-		if (s_misc[10 + ((it + 1) & 1)]) {
-			repair(pprev, b, b, b);
-			load_tile(cur);
-			if (tid == 0) s_misc[10 + ((it + 1) & 1)] = 0;
-		}
-		/* P2 */
-		if (tid < RADIX) {
-			u32 c[WARPS];
-#pragma unroll
-			for (int w = 0; w < WARPS; ++w) c[w] = whist[w * RADIX + tid];
-			u32 count = 0;
-#pragma unroll
-			for (int w = 0; w < WARPS; ++w) count += c[w];
-			st_relaxed(agg + (size_t) cur * RADIX + tid, (LbT) (PPWord<LbT>::VALID | (LbT) count));
-			const u32 incl = warp_inclusive_scan<u32>(count, lane);
-			if (lane == 31) s_misc[warp] = incl;
-			named_bar_sync(1, RADIX);
-			u32 off = 0;
-#pragma unroll
-			for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[w];
-			u32 run = off + incl - count;
-			s_ds[b * RADIX + tid] = run;
-#pragma unroll
-			for (int w = 0; w < WARPS; ++w) { whist[w * RADIX + tid] = run; run += c[w]; }
-		} else if (is_pref_thread) {
-			u32 nt = 0;
-			if (tid == RADIX) nt = atomicAdd(ticket, 1u);        /* in flight during the prefix wait */
-			if (prev != NONE) prefix_to_goff(prev, b ^ 1, b ^ 1, wp);
-			if (tid == RADIX) s_misc[8] = nt;
-		}
-		mark(2);
-		__syncthreads();                                         /* B2 */
-		mark(3);
-		/* P3 place */
-		{
-			ElemT* skeys = s_buf + (size_t) b * TILE;
-			if (cnt == (u32) TILE) {
-#pragma unroll
-				for (int i = 0; i < IPT; ++i) {
-					const u32 p = atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
-					if (ABL != 3 || p == 0xffffffffu) skeys[p] = key[i];
-				}
-			} else {
-#pragma unroll
-				for (int i = 0; i < IPT; ++i)
-					if (wbase + i * 32u < cnt)
-						skeys[atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u)] = key[i];
-			}
-			__syncwarp();
-			zero_row();
-		}
-		mark(4);
-		/* P4 next tile */
-		const u32 nxt = s_misc[8];
-		const bool more = nxt < num_tiles;
-		if (more) load_tile(nxt);
-		mark(5);
-		/* P5 write-out of the previous tile */
-		if (prev != NONE) {
-			if (write_out(prev, b ^ 1, b ^ 1, true)) s_misc[10 + (it & 1)] = 1;
-		}
-		mark(6);
-		pprev = prev;
-		prev = cur;
-		b ^= 1;
-		++it;
-		if (!more) break;
-		cur = nxt;
-	}
-	/* ---- epilogue: `prev` is staged in buffer b^1; pprev was written in the last iteration */
-	__syncthreads();
-	if (s_misc[10 + ((it + 1) & 1)]) repair(pprev, b, b, b);
-	{ const LbT zw[DPT] = {}; if (tid >= RADIX) prefix_to_goff(prev, b ^ 1, b ^ 1, zw); }
-	__syncthreads();
-	const bool bad = write_out(prev, b ^ 1, b ^ 1, true);
-	if (__syncthreads_or(bad ? 1 : 0)) repair(prev, b ^ 1, b ^ 1, b ^ 1);
 	}
 }
 
-template <typename ElemT, int THREADS, int IPT, typename LbT>
+template <typename ElemT, int THREADS, int IPT, typename LbT, bool HAS_VAL = false>
 constexpr size_t onesweep_v6_smem() {
 	constexpr size_t worker = (size_t) (THREADS / 32) * RADIX * 4 + 4 * RADIX * 4 + 2 * RADIX * 8 + 16 * 4 +
-		2 * (size_t) THREADS * IPT * sizeof(ElemT);
-	constexpr size_t prop = pp_propagate2_smem<LbT, THREADS, v6_prop_groups(THREADS)>();
+		2 * ((size_t) THREADS * IPT * sizeof(ElemT) + (HAS_VAL ? (size_t) THREADS * IPT * 6 : 0));
+	constexpr size_t prop = pp_propagate2_smem<LbT, THREADS, v6_prop_groups(THREADS, (int) sizeof(LbT))>();
 	return worker > prop ? worker : prop;
 }
 

@@ -86,9 +86,10 @@ int clo_radix_get_timing(CloRadixState* st, float* out_ms, int cap);
 /* device status flag of the last radix call (0 = ok); synchronises the stream */
 int clo_radix_status(CloRadixState* st, cudaStream_t stream);
 
-/* One keys-only onesweep pass with the two-barrier persistent kernel (radix_v6.cu).
+/* One onesweep pass (keys, or keys + u32 payload) with the persistent v6 kernel (radix_v6.cu).
  * elem_size 4 or 8; wide selects 64-bit AGG/PREF words; tile must equal the kernel's tile. */
-cudaError_t clo_radix_v6_pass(int elem_size, int wide, int tile, const void* in, void* out, size_t n,
+cudaError_t clo_radix_v6_pass(int elem_size, int wide, int tile, const void* in, void* out,
+		const uint32_t* payload_in, uint32_t* payload_out, size_t n,
 		void* agg, void* pref, uint32_t* ticket, const unsigned long long* bins, uint32_t start_bit,
 		uint32_t dmask, int* err, int sm_count, int prof_on, int flags, cudaStream_t stream);
 

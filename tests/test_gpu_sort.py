@@ -324,3 +324,35 @@ def test_sample_sort_two_gpus_fused_exchange():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DIST GPU OK" in r.stdout
+
+
+@pytest.mark.parametrize("et,with_payload", [(oracle.UINT, False), (oracle.ULONG, False), (oracle.UINT, True), (oracle.ULONG, True)])
+def test_satradix_wide_lookback_words(clo, ctx, queue, et, with_payload, monkeypatch):
+    """n >= 2^31 switches the tile-prefix words to 64 bits; CLO_RADIX_WIDE=1 forces that path at
+    a testable size (keys only and keys + payload, stable)."""
+    import torch
+    monkeypatch.setenv("CLO_RADIX_WIDE", "1")
+    rng = np.random.default_rng(5 + et)
+    n = (1 << 20) + 999
+    a = _rand(rng, et, n)
+    a[: n // 2] &= 0xFF                        # many equal keys: stability matters
+    s = clo.CloSort("satradix", ctx, et)
+    if not with_payload:
+        got = s.with_host_data(a, queue)
+        assert np.array_equal(got, np.sort(a))
+    else:
+        sdt = np.int32 if a.dtype.itemsize == 4 else np.int64
+        tk = torch.from_numpy(a.view(sdt).copy()).cuda()
+        tp = torch.arange(n, dtype=torch.int32, device="cuda")
+        bk, bp = clo.Buffer.wrap_tensor(ctx, tk), clo.Buffer.wrap_tensor(ctx, tp)
+        s.pairs_with_device_data(queue, bk, bp, n)
+        queue.finish()
+        order = np.argsort(a, kind="stable")
+        assert np.array_equal(tk.cpu().numpy().view(a.dtype), a[order])
+        assert np.array_equal(tp.cpu().numpy().view(np.uint32), order.astype(np.uint32))
+        bk.destroy(); bp.destroy()
+    dbg = s.debug(queue)
+    s.destroy()
+    monkeypatch.delenv("CLO_RADIX_WIDE")
+    clo.CloSort("satradix", ctx, et).destroy()
+    assert dbg[0] == 0
