@@ -51,20 +51,35 @@ __device__ __forceinline__ void pt_load_splitters(PtSplitters<ElemT, NS>& sp, co
 	}
 }
 
-/* bucket = number of splitters (key, index) <= (k, g).  The index only matters for a key
- * that EQUALS a splitter key, so the 64-bit tie-break runs only when some lane needs it. */
+/* compile-time-indexed element of a register array chosen by a run-time index (select chain) */
+template <typename T, int N>
+__device__ __forceinline__ T pt_pick(const T (&a)[N], u32 idx, int stride, int first) {
+	T v = a[first];
+#pragma unroll
+	for (int j = first + stride; j < N; j += stride) if (idx >= (u32) (j - first)) v = a[j];
+	return v;
+}
+
+/* bucket = number of splitters (key, index) <= (k, g).  The splitter keys are sorted, so the
+ * number of keys < k is a branch-free binary search over the NS = 2^m - 1 register-resident
+ * splitters; the search always compares k with the first splitter key >= k, so "some pivot
+ * equalled k" detects exactly the keys whose bucket depends on the 64-bit index tie-break,
+ * which then (and only then, for the whole warp) runs the linear rule. */
 template <typename ElemT, int NS>
 __device__ __forceinline__ u32 pt_bucket(ElemT k, u64 g, const PtSplitters<ElemT, NS>& sp) {
 	u32 b = 0;
 	bool tie = false;
 #pragma unroll
-	for (int s = 0; s < NS; ++s) {
-		b += sp.key[s] < k ? 1u : 0u;
-		tie |= sp.key[s] == k;
+	for (int step = (NS + 1) / 2; step >= 1; step >>= 1) {
+		/* candidates at this level: indices step-1, step-1 + 2*step, ... ; b is a multiple of 2*step */
+		const ElemT pivot = pt_pick<ElemT, NS>(sp.key, b, 2 * step, step - 1);
+		tie |= pivot == k;
+		if (pivot < k) b += (u32) step;
 	}
 	if (__any_sync(__activemask(), tie)) {
+		b = 0;
 #pragma unroll
-		for (int s = 0; s < NS; ++s) b += (sp.key[s] == k && sp.idx[s] <= g) ? 1u : 0u;
+		for (int s = 0; s < NS; ++s) b += (sp.key[s] < k || (sp.key[s] == k && sp.idx[s] <= g)) ? 1u : 0u;
 	}
 	return b;
 }
@@ -205,13 +220,15 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 			const bool valid = i < hi;
 			u32 b = pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp);
 			if (!valid) b = 0xffffffffu;
-			u32 mine = 0, add = 0;
+			/* lanes of my bucket / lanes of bucket `lane`: one ballot per bucket BIT */
+			u32 mine = __ballot_sync(0xffffffffu, valid), forq = mine;
 #pragma unroll
-			for (u32 q = 0; q < (u32) NB; ++q) {
-				const u32 m = __ballot_sync(0xffffffffu, b == q);
-				if (b == q) mine = m;
-				if ((u32) lane == q) add = __popc(m);
+			for (int j = 0; (1 << j) < NB; ++j) {
+				const u32 bj = __ballot_sync(0xffffffffu, (b >> j) & 1u);
+				mine &= ((b >> j) & 1u) ? bj : ~bj;
+				forq &= ((lane >> j) & 1) ? bj : ~bj;
 			}
+			const u32 add = lane < NB ? __popc(forq) : 0u;
 			/* append to the ring of my bucket */
 			const u32 tail = __shfl_sync(0xffffffffu, head + cnt, valid ? (int) b : 0);
 			if (valid) {

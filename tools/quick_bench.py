@@ -90,6 +90,25 @@ def main():
         b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out
         torch.cuda.empty_cache()
 
+    if "partition" in what:
+        # the sample sort's stable 8-way partition, local destinations (one GPU): count + offsets + scatter
+        n = 1 << args.log2n_sort
+        P = 8
+        t_in = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
+        t_out = torch.empty_like(t_in)
+        spl = torch.tensor([(i * (1 << 32) // P) - (1 << 32 if i * (1 << 32) // P >= (1 << 31) else 0) for i in range(1, P)], dtype=torch.int32, device="cuda")
+        spi = torch.zeros(P - 1, dtype=torch.int64, device="cuda")
+        cnt = torch.zeros(P, dtype=torch.int64, device="cuda")
+        W = clo.Buffer.wrap_tensor
+        b = [W(ctx, t_in), W(ctx, t_out), W(ctx, spl), W(ctx, spi), W(ctx, cnt)]
+        s = clo.CloSort("satradix", ctx, clo.UINT)
+        med, best = timed(lambda: s.partition_with_device_data(q, b[0], None, b[1], None, n, 0, b[2], b[3], P, b[4]), args.iters)
+        print(json.dumps({"partition_u32_8way": dict(n=n, ms=med, gkeys=n / med / 1e6, gbs=12.0 * n / med / 1e6, frac=12.0 * n / med / 1e6 / peak,
+                                                    counts=cnt.tolist())}), flush=True)
+        for x in b:
+            x.destroy()
+        s.destroy()
+
     if "sortcfg" in what:
         # tuning sweep of the headline kernel: tile configuration x match method
         n = 1 << args.log2n_sort
