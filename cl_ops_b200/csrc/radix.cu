@@ -503,7 +503,7 @@ clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 template <typename ElemT, bool HAS_VAL> struct TileCfg {
 	/* keys-only: 512 x 16 (4 B and narrower), 512 x 8 (8 B); with payload: 512 x 12 / 512 x 8 */
 	static const int THREADS = 512;
-	static const int IPT = HAS_VAL ? (sizeof(ElemT) == 8 ? 6 : 8) : (sizeof(ElemT) == 8 ? 8 : 16);
+	static const int IPT = HAS_VAL ? (sizeof(ElemT) == 8 ? 6 : 8) : (sizeof(ElemT) == 8 ? 10 : 16);
 };
 
 template <typename ElemT, bool HAS_VAL, int THREADS, int IPT, bool USE_INFO = true>

@@ -8,6 +8,7 @@
 //   5 ATOMS.ADD with return, packed u16 pairs, warp-private [128] words
 //   6 ATOMS.ADD with return, CTA-shared [256] table
 //   7 LDS.64 random (digit -> 8-byte entry)
+//   8 SHFL.UP, 9 SHFL.UP + LDS linear (do shuffles share the shared-memory data pipe?)
 // Output: SM cycles per warp instruction (lower bound on what a pass pays per 32 keys).
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o ubench_smem tools/ubench_smem.cu
 #include <cstdio>
@@ -36,6 +37,8 @@ __global__ void __launch_bounds__(256) k_smem(unsigned* out, int iters, unsigned
 			else if (MODE == 5) acc += atomicAdd(&wt[d >> 1], (d & 1) ? 65536u : 1u);
 			else if (MODE == 6) acc += atomicAdd(&tab[d], 1u);
 			else if (MODE == 7) { uint2 v = reinterpret_cast<uint2*>(wt)[d & 127]; acc += v.x ^ v.y; }
+			else if (MODE == 8) acc += __shfl_up_sync(0xffffffffu, x[i], 1);
+			else if (MODE == 9) { acc += __shfl_up_sync(0xffffffffu, x[i], 1); acc += tab[(threadIdx.x + 256 * i + it * 32) & 8191]; }
 			x[i] = x[i] * 1664525u + 1013904223u;
 		}
 	}
@@ -68,6 +71,8 @@ int main() {
 	run<5, 8>("ATOMS.ADD ret packed u16", d_out, mhz);
 	run<6, 8>("ATOMS.ADD ret, CTA-shared table", d_out, mhz);
 	run<7, 8>("LDS.64 random", d_out, mhz);
+	run<8, 8>("SHFL.UP", d_out, mhz);
+	run<9, 8>("SHFL.UP + LDS linear (2 ops: same pipe if ~sum)", d_out, mhz);
 	printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
 	return 0;
 }
