@@ -30,10 +30,13 @@ def main():
             g0 = sum(n_all[:r])
             payload = (torch.arange(n, dtype=torch.int64, device="cuda") + g0).to(torch.int32) if with_payload else None
             ops = cdist.GpuOps(clo, ctx, q, key_type)
-            ops.setup_peer_exchange(int(1.5 * max(n_all)), kdt, with_payload)
+            # receive buffers too small for the uniform u32 case: the scatter must be a no-op and
+            # the NCCL all-to-all-v path must take over
+            tiny = (bits == 32 and not dup)
+            ops.setup_peer_exchange(1000 if tiny else int(1.5 * max(n_all)), kdt, with_payload)
             for call in range(2):            # second call reuses the receive buffers
                 out_k, out_p, info = cdist.sample_sort(keys, payload, ops, bits, gidx0=None if call else g0)
-                assert info.get("fused"), "fused path not taken"
+                assert bool(info.get("fused")) == (not tiny), "wrong exchange path"
                 # reference: gather everything, stable sort by unsigned key
                 gk = [torch.empty(m, dtype=kdt, device="cuda") for m in n_all]
                 dist.all_gather(gk, keys)
