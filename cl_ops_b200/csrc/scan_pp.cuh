@@ -175,7 +175,7 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 	extern __shared__ __align__(16) unsigned char spp_smem[];
 	ElemT* ring = reinterpret_cast<ElemT*>(spp_smem);            /* [S][TILE] */
 	__shared__ u32 s_tile[S];
-	__shared__ IntraT s_wsum[S][WARPS];         /* per-warp tile sums: tile-local, so IntraT */
+	__shared__ AccT s_wsum[S][WARPS];
 	__shared__ AccT s_pref;
 
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -237,14 +237,14 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 				for (int c = 0; c < EPV; ++c) sum += to_acc<ElemT, SumT, IntraT>(e[c]);
 			}
 			sum = warp_reduce_sum<IntraT>(sum);
-			if (lane == 0) s_wsum[r % S][warp] = sum;
+			if (lane == 0) s_wsum[r % S][warp] = static_cast<AccT>(sum);
 		}
 		__syncthreads();
 		if (r >= 0 && t_red < num_tiles && tid == 0) {
-			IntraT total = IntraT(0);
+			AccT total = AccT(0);
 #pragma unroll
 			for (int w = 0; w < WARPS; ++w) total += s_wsum[r % S][w];
-			spp_publish<AccT>(agg + (size_t) t_red * AW::N, epoch, static_cast<AccT>(total));
+			spp_publish<AccT>(agg + (size_t) t_red * AW::N, epoch, total);
 		}
 
 		/* (4) scan + store the tile whose prefix was requested LAG iterations ago */
@@ -261,18 +261,10 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 			const ElemT* src = ring + (size_t) (q % S) * TILE;
 			const size_t base = (size_t) t_scan * TILE;
 			const bool full = base + TILE <= n;
-			IntraT lower = IntraT(0);
+			AccT warp_off = s_pref;
 #pragma unroll
-			for (int w = 0; w < WARPS; ++w) if (w < warp) lower += s_wsum[q % S][w];
-			const AccT warp_off = s_pref + static_cast<AccT>(lower);
+			for (int w = 0; w < WARPS; ++w) if (w < warp) warp_off += s_wsum[q % S][w];
 			AccT row_off = warp_off;
-			/* f32 sums: the f64 base of this warp's rows is split ONCE per tile into an f32
-			 * head and an f32 remainder; the rows then run entirely in f32 (no per-vector
-			 * f64 conversions or adds).  The result is hi + (local + lo): one rounding of
-			 * the local part (<= 4096 elements) and one final rounding, ~1e-7 relative. */
-			const float f_hi = static_cast<float>(warp_off);
-			const float f_lo = static_cast<float>(warp_off - static_cast<AccT>(f_hi));
-			float f_row = 0.0f;
 #pragma unroll
 			for (int j = 0; j < VPT; ++j) {
 				const u32 o = lane_off + (u32) j * 32 * EPV;
@@ -287,16 +279,16 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 				IntraT excl = __shfl_up_sync(0xffffffffu, incl, 1);
 				if (lane == 0) excl = IntraT(0);
 				const IntraT row_total = __shfl_sync(0xffffffffu, incl, 31);
+				const AccT b = row_off + static_cast<AccT>(excl);
+				row_off += static_cast<AccT>(row_total);
 				SumT ov[EPV];
 				if (std::is_same<SumT, float>::value) {
-					const float l = (f_row + static_cast<float>(excl)) + f_lo;
-					f_row += static_cast<float>(row_total);
-					ov[0] = static_cast<SumT>(f_hi + l);
+					/* round the f64 base once per vector; one more f32 rounding per element */
+					const IntraT bf = static_cast<IntraT>(b);
+					ov[0] = static_cast<SumT>(bf);
 #pragma unroll
-					for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(f_hi + (l + static_cast<float>(v[c - 1])));
+					for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(bf + v[c - 1]);
 				} else {
-					const AccT b = row_off + static_cast<AccT>(excl);
-					row_off += static_cast<AccT>(row_total);
 					ov[0] = static_cast<SumT>(b);
 #pragma unroll
 					for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(b + static_cast<AccT>(v[c - 1]));
