@@ -24,6 +24,7 @@ struct clo_sort {
 	unsigned minps, maxps, maxsfs;  /* abitonic options, kept as hints */
 	CloRadixState* rs;
 	CloBitonicState* bs;
+	CloJitSort* jit;         /* run-time compiled network for compare / get_key strings outside the menu */
 };
 
 static ccl_program g_sort_program = { "clo_sort (precompiled sm_100a)" };
@@ -284,7 +285,9 @@ static CCLEvent* bitonic_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exe
 		rc = cudaMemcpyAsync(data_out->ptr, data_in->ptr, bytes, cudaMemcpyDeviceToDevice, cq_exec->stream);
 		work = data_out->ptr;
 	}
-	if (rc == cudaSuccess)
+	if (rc == cudaSuccess && sorter->jit)
+		rc = clo_jit_bitonic_sort(sorter->jit, clo_type_sizeof(sorter->elem_type), work, numel, cq_exec->stream);
+	else if (rc == cudaSuccess)
 		rc = clo_bitonic_sort(sorter->bs, clo_type_sizeof(sorter->elem_type), sorter->ks, work, numel, cq_exec->stream);
 	clo_queue_end(cq_exec, evt);
 	if (clo_cuda_failed(rc, err, "clo_bitonic_sort")) return NULL;
@@ -340,7 +343,8 @@ static CCLEvent* gselect_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exe
 		out = tmp;
 	}
 	ccl_event* evt = clo_queue_begin(cq_exec, "clo_gselect");
-	cudaError_t rc = clo_gselect_sort(es, sorter->ks, data_in->ptr, out, numel, cq_exec->stream);
+	cudaError_t rc = sorter->jit ? clo_jit_gselect_sort(sorter->jit, data_in->ptr, out, numel, cq_exec->stream)
+		: clo_gselect_sort(es, sorter->ks, data_in->ptr, out, numel, cq_exec->stream);
 	if (rc == cudaSuccess && tmp)
 		rc = cudaMemcpyAsync(data_in->ptr, tmp, bytes, cudaMemcpyDeviceToDevice, cq_exec->stream);
 	if (tmp) cudaFreeAsync(tmp, cq_exec->stream);
@@ -401,17 +405,31 @@ extern "C" CloSort* clo_sort_new(const char* type, const char* options, CCLConte
 	s->radix = 16; s->minps = 1; s->maxps = 4; s->maxsfs = 0xffffffffu;
 	s->rs = clo_radix_state_new();
 	s->bs = clo_bitonic_state_new();
+	s->jit = NULL;
 
 	GError* ierr = NULL;
 	uint32_t shift = 0; uint64_t mask = ~0ull; int desc = 0;
 	s->impl_def.init(s, options, &ierr);
-	if (!ierr && !parse_get_key(get_key, shift, mask))
-		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
-			"get_key '%s' is not supported (menu: (x), ((x) >> K), ((x) & M), (((x) >> K) & M))", get_key);
-	if (!ierr && !parse_compare(compare, desc))
-		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
-			"compare '%s' is not supported (menu: ((a) > (b)), ((a) < (b)))", compare);
-	if (!ierr && kind_of(et) == CLO_KIND_FLOAT && (shift != 0 || mask != ~0ull || kt != et))
+	const bool in_menu = parse_get_key(get_key, shift, mask) && parse_compare(compare, desc);
+	const bool comparison_sort = def != &clo_sort_satradix_def;
+	if (!ierr && !in_menu && comparison_sort) {
+		/* the reference compiles ANY macro body into its kernels (clo_sort_abstract.c:144-168);
+		 * strings outside the precompiled menu are compiled here too, with NVRTC */
+		std::string msg;
+		CloDeviceGuard g(ctx->dev.ordinal);
+		s->jit = clo_jit_sort_new(et, kt, compare, get_key, msg);
+		if (!s->jit) g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg.c_str());
+		shift = 0; mask = ~0ull; desc = 0;
+	}
+	if (!ierr && !in_menu && !comparison_sort) {
+		if (!parse_get_key(get_key, shift, mask))
+			g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
+				"get_key '%s' is not supported by satradix (menu: (x), ((x) >> K), ((x) & M), (((x) >> K) & M))", get_key);
+		else
+			g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
+				"compare '%s' is not supported by satradix (menu: ((a) > (b)), ((a) < (b)))", compare);
+	}
+	if (!ierr && !s->jit && kind_of(et) == CLO_KIND_FLOAT && (shift != 0 || mask != ~0ull || kt != et))
 		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS, "a floating-point element only supports the identity key");
 	if (ierr) { g_propagate_error(err, ierr); clo_sort_destroy(s); return NULL; }
 
@@ -437,6 +455,7 @@ extern "C" void clo_sort_destroy(CloSort* sorter) {
 		CloDeviceGuard g(sorter->ctx->dev.ordinal);
 		clo_radix_state_free(sorter->rs);
 		clo_bitonic_state_free(sorter->bs);
+		clo_jit_sort_free(sorter->jit);
 	}
 	ccl_context_unref(sorter->ctx);
 	delete sorter;

@@ -113,4 +113,15 @@ cudaError_t clo_radix_partition_scatter(CloRadixState* st, size_t elem_size, con
 		const uint64_t* first_slot, void* const* dests, void* const* vdests, const int* ok,
 		cudaStream_t stream, const char** err_msg);
 
+/* run-time compiled comparison sorts for macro strings outside the precompiled menu (jit.cu) */
+#ifdef __cplusplus
+#include <string>
+struct CloJitSort;
+CloJitSort* clo_jit_sort_new(CloType elem_type, CloType key_type, const char* compare, const char* get_key, std::string& msg);
+void clo_jit_sort_free(CloJitSort* j);
+const char* clo_jit_sort_source(CloJitSort* j);
+cudaError_t clo_jit_bitonic_sort(CloJitSort* j, size_t elem_size, void* data, size_t n, cudaStream_t stream);
+cudaError_t clo_jit_gselect_sort(CloJitSort* j, const void* in, void* out, size_t n, cudaStream_t stream);
+#endif
+
 #endif

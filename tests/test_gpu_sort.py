@@ -217,7 +217,7 @@ def test_sort_errors(clo, ctx):
             clo.CloSort("abitonic", ctx, oracle.UINT, **kw)
         assert ei.value.code == clo.CLO_ERROR_ARGS
     with pytest.raises(clo.CloError) as ei:
-        clo.CloSort("sbitonic", ctx, oracle.UINT, compare="((a) >= (b))")
+        clo.CloSort("satradix", ctx, oracle.UINT, compare="((a) >= (b))")
     assert ei.value.code == clo.CLO_ERROR_ARGS
     s = clo.CloSort("satradix", ctx, oracle.UINT)
     assert s.kernel_names() == ["clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep"]
@@ -356,3 +356,74 @@ def test_satradix_wide_lookback_words(clo, ctx, queue, et, with_payload, monkeyp
     monkeypatch.delenv("CLO_RADIX_WIDE")
     clo.CloSort("satradix", ctx, et).destroy()
     assert dbg[0] == 0
+
+
+def _np_bitonic_network(a, key, after):
+    """The canonical network (clo_sort_sbitonic.cl:38-69 + host loop clo_sort_sbitonic.c:73-118)
+    in numpy, for an arbitrary key(x) and after(ka, kb); n padded to a power of two with
+    elements that come after everything."""
+    n = len(a)
+    np2 = 1
+    while np2 < n:
+        np2 <<= 1
+    d = np.concatenate([a, np.zeros(np2 - n, dtype=a.dtype)])
+    pad = np.concatenate([np.zeros(n, dtype=bool), np.ones(np2 - n, dtype=bool)])
+    log = int(np.log2(np2)) if np2 > 1 else 0
+    p = np.arange(np2 // 2)
+    for stage in range(1, log + 1):
+        desc = ((p >> (stage - 1)) & 1).astype(bool)
+        for step in range(stage, 0, -1):
+            stride = 1 << (step - 1)
+            i1 = p + (p // stride) * stride
+            i2 = i1 + stride
+            c = after(key(d[i1]), key(d[i2]))
+            must = (pad[i1] & ~pad[i2]) | ((pad[i1] == pad[i2]) & c)
+            sw = must != desc
+            x, y = d[i1][sw].copy(), d[i2][sw].copy()
+            d[i1[sw]], d[i2[sw]] = y, x
+            px, py = pad[i1][sw].copy(), pad[i2][sw].copy()
+            pad[i1[sw]], pad[i2[sw]] = py, px
+    return d[:n]
+
+
+@pytest.mark.parametrize("alg", ["sbitonic", "abitonic"])
+@pytest.mark.parametrize("n", [1, 2, 1000, 4096, 5000])
+def test_custom_macro_strings_are_compiled_at_run_time(clo, ctx, queue, alg, n):
+    """compare / get_key strings outside the precompiled menu: spliced into the network and built
+    with NVRTC, as the reference builds them into its OpenCL kernels (clo_sort_abstract.c:144-168)."""
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 2**32, size=n, dtype=np.uint64).astype(np.uint32)
+    s = clo.CloSort(alg, ctx, oracle.UINT, key_type=oracle.UCHAR,
+                    compare="(((a) & 15) > ((b) & 15))", get_key="(((x) >> 3) ^ (x))")
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    key = lambda x: ((x >> np.uint32(3)) ^ x).astype(np.uint8)
+    after = lambda ka, kb: (ka & 15) > (kb & 15)
+    assert np.array_equal(got, _np_bitonic_network(a, key, after))
+
+
+def test_custom_macro_strings_gselect_and_errors(clo, ctx, queue):
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 1000, size=3001).astype(np.uint32)
+    # gselect ranks by COMPARE plus KEY equality (clo_sort_gselect.cl:44-56), so the comparator must be a
+    # strict order on the keys: descending by the scrambled key, equal elements in input order
+    s = clo.CloSort("gselect", ctx, oracle.UINT, compare="((a) < (b))", get_key="((x) * 40503u % 65521u)")
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    k = (a.astype(np.uint64) * 40503 % (1 << 32) % 65521).astype(np.int64)
+    order = np.argsort(-k, kind="stable")
+    assert np.array_equal(got, a[order])
+    # a float element with a custom comparator (descending by magnitude)
+    f = ((rng.random(2048) - 0.5) * 100).astype(np.float32)
+    s = clo.CloSort("sbitonic", ctx, oracle.FLOAT, compare="(fabsf(a) < fabsf(b))")
+    got = s.with_host_data(f, queue)
+    s.destroy()
+    assert np.array_equal(got, _np_bitonic_network(f, lambda x: x, lambda ka, kb: np.abs(ka) < np.abs(kb)))
+    # strings that do not compile are an argument error carrying the compiler's message
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloSort("sbitonic", ctx, oracle.UINT, compare="((a) >>> (b))")
+    assert ei.value.code == clo.CLO_ERROR_ARGS and "do not compile" in str(ei.value)
+    # the radix sort has no comparator to splice: still the menu only
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloSort("satradix", ctx, oracle.UINT, get_key="((x) * 3)")
+    assert ei.value.code == clo.CLO_ERROR_ARGS
