@@ -49,8 +49,14 @@ struct ccl_buffer {
 	bool ipc = false;      /* ptr came from cudaIpcOpenMemHandle */
 };
 
+struct ccl_kernel;
 struct ccl_program {
 	const char* tag;
+	/* run-time compiled programs (ccl_program_new_from_source, jit.cu); unused by the static tags */
+	ccl_context* ctx = nullptr;
+	std::string source;
+	void* module = nullptr;
+	std::vector<ccl_kernel*> kernels;
 };
 
 struct ccl_prof {

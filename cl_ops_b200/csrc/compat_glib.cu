@@ -58,11 +58,46 @@ gboolean g_str_has_prefix(const gchar* s, const gchar* prefix) {
 
 gint g_ascii_strncasecmp(const gchar* a, const gchar* b, gsize n) { return strncasecmp(a, b, n); }
 
+static GPrintFunc g_print_handler = NULL;
+
+GPrintFunc g_set_print_handler(GPrintFunc func) {
+	GPrintFunc old = g_print_handler;
+	g_print_handler = func;
+	return old;
+}
+
 void g_print(const gchar* format, ...) {
 	va_list ap;
 	va_start(ap, format);
-	vfprintf(stdout, format, ap);
+	if (g_print_handler) {
+		char buf[4096];
+		vsnprintf(buf, sizeof(buf), format, ap);
+		g_print_handler(buf);
+	} else {
+		vfprintf(stdout, format, ap);
+	}
 	va_end(ap);
+}
+
+/* ---- test harness */
+struct clo_gtest { const char* path; GTestFunc fn; };
+static clo_gtest g_tests[64];
+static int g_ntests = 0;
+
+void g_test_init(int* argc, char*** argv, ...) { (void) argc; (void) argv; }
+
+void g_test_add_func(const char* testpath, GTestFunc test_func) {
+	if (g_ntests < 64) { g_tests[g_ntests].path = testpath; g_tests[g_ntests].fn = test_func; ++g_ntests; }
+}
+
+int g_test_run(void) {
+	for (int i = 0; i < g_ntests; ++i) {
+		printf("%s: ", g_tests[i].path);
+		fflush(stdout);
+		g_tests[i].fn();             /* a failing g_assert aborts, as in GLib */
+		printf("OK\n");
+	}
+	return 0;
 }
 
 void clo_b200_g_debug(const gchar* format, ...) {
@@ -217,7 +252,7 @@ gboolean g_option_context_parse(GOptionContext* c, gint* argc, gchar*** argv, GE
 		char* a = (*argv)[i];
 		const GOptionEntry* e = NULL;
 		const char* inline_val = NULL;
-		if (strcmp(a, "--help") == 0 || strcmp(a, "-h") == 0 || strcmp(a, "-?") == 0) {
+		if (strcmp(a, "--help") == 0 || strcmp(a, "-?") == 0 || (strcmp(a, "-h") == 0 && !find_entry(c, NULL, 0, 'h'))) {
 			printf("Usage:\n  %s [OPTION...]%s\n\nApplication Options:\n", (*argv)[0], c->summary);
 			if (c->entries)
 				for (const GOptionEntry* q = c->entries; q->long_name; ++q)

@@ -18,6 +18,8 @@
 #include "sort_common.h"
 
 #include <dlfcn.h>
+#include <cstdarg>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -257,4 +259,232 @@ cudaError_t clo_jit_gselect_sort(CloJitSort* j, const void* in, void* out, size_
 	if (driver().LaunchKernel(j->f_gselect, (unsigned) ((n + 255) / 256), 1, 1, 256, 1, 1, 0, stream, args, nullptr) != 0) return cudaErrorLaunchFailure;
 	CLO_COUNT_LAUNCH(1);
 	return cudaSuccess;
+}
+
+/* =====================================================================================
+ * cf4ocl2 program / kernel objects on NVRTC: what the reference's clo_rng_bench.c:176-312 and
+ * tests/test_rng.c:85-118 do with the source string of clo_rng_get_source() -- concatenate a
+ * small OpenCL C kernel, build it, set its arguments, enqueue it.  The kernel text is OpenCL C;
+ * the prelude below maps the handful of OpenCL spellings those kernels use onto CUDA C.
+ * ===================================================================================== */
+namespace {
+
+const char kOclPrelude[] = R"SRC(
+#define __kernel extern "C" __global__
+#define __global
+#define __constant const
+#define __private
+#define __local __shared__
+typedef unsigned char uchar;
+typedef unsigned short ushort;
+typedef unsigned int uint;
+typedef unsigned long long ulong;
+#ifndef UINT_MAX
+#define UINT_MAX 0xffffffffu
+#endif
+#ifndef INT_MAX
+#define INT_MAX 2147483647
+#endif
+__device__ __forceinline__ unsigned long long get_global_id(int d) { return d == 0 ? (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x : 0; }
+__device__ __forceinline__ unsigned long long get_local_id(int d) { return d == 0 ? threadIdx.x : 0; }
+__device__ __forceinline__ unsigned long long get_group_id(int d) { return d == 0 ? blockIdx.x : 0; }
+__device__ __forceinline__ unsigned long long get_local_size(int d) { return d == 0 ? blockDim.x : 1; }
+__device__ __forceinline__ unsigned long long get_global_size(int d) { return d == 0 ? (unsigned long long) gridDim.x * blockDim.x : 1; }
+)SRC";
+
+struct ArgSlot { std::vector<unsigned char> bytes; };
+
+} // namespace
+
+struct ccl_arg { unsigned magic; std::vector<unsigned char> bytes; };
+struct ccl_kernel {
+	ccl_program* prg;
+	CUfunction fn;
+	std::string name;
+	std::vector<ArgSlot> args;
+};
+
+extern "C" CCLProgram* ccl_program_new_from_source(CCLContext* ctx, const char* src, GError** err) {
+	if (!ctx || !src) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "ccl_program_new_from_source: NULL argument"); return NULL; }
+	ccl_program* p = new ccl_program();
+	p->tag = "run-time compiled (NVRTC, sm_100a)";
+	p->ctx = ctx;
+	p->source = src;
+	ccl_context_ref(ctx);
+	clo_handle_add(p);
+	return p;
+}
+
+extern "C" cl_bool ccl_program_build(CCLProgram* prg, const char* options, GError** err) {
+	if (!prg || !prg->ctx) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "ccl_program_build: not a source program"); return CL_FALSE; }
+	Nvrtc& rt = nvrtc();
+	Driver& drv = driver();
+	if (!rt.ok || !drv.ok) { g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "building a program needs NVRTC and the CUDA driver"); return CL_FALSE; }
+	/* OpenCL build options: only the -D definitions have a meaning here */
+	std::vector<std::string> defs;
+	if (options) {
+		std::string o(options);
+		size_t i = 0;
+		while ((i = o.find("-D", i)) != std::string::npos) {
+			i += 2;
+			while (i < o.size() && o[i] == ' ') ++i;
+			size_t e = i;
+			while (e < o.size() && o[e] != ' ') ++e;
+			if (e > i) defs.push_back("-D" + o.substr(i, e - i));
+			i = e;
+		}
+	}
+	std::vector<const char*> opts = { "--gpu-architecture=sm_100a", "--std=c++17", "-default-device" };
+	for (const std::string& d : defs) opts.push_back(d.c_str());
+	const std::string full = std::string(kOclPrelude) + prg->source;
+	nvrtcProgram np = nullptr;
+	if (rt.CreateProgram(&np, full.c_str(), "clo_program.cu", 0, nullptr, nullptr) != 0) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "nvrtcCreateProgram failed");
+		return CL_FALSE;
+	}
+	if (rt.CompileProgram(np, (int) opts.size(), opts.data()) != 0) {
+		size_t ls = 0;
+		rt.GetProgramLogSize(np, &ls);
+		std::vector<char> log(ls + 1, 0);
+		if (ls) rt.GetProgramLog(np, log.data());
+		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "program build failed: %s", log.data());
+		rt.DestroyProgram(&np);
+		return CL_FALSE;
+	}
+	size_t cs = 0;
+	rt.GetCUBINSize(np, &cs);
+	std::vector<char> cubin(cs);
+	rt.GetCUBIN(np, cubin.data());
+	rt.DestroyProgram(&np);
+	CloDeviceGuard g(prg->ctx->dev.ordinal);
+	cudaFree(0);
+	CUmodule mod = nullptr;
+	if (drv.ModuleLoadData(&mod, cubin.data()) != 0) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "loading the built program failed");
+		return CL_FALSE;
+	}
+	prg->module = mod;
+	return CL_TRUE;
+}
+
+extern "C" CCLKernel* ccl_program_get_kernel(CCLProgram* prg, const char* name, GError** err) {
+	if (!prg || !prg->module || !name) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "ccl_program_get_kernel: program not built"); return NULL; }
+	for (ccl_kernel* k : prg->kernels) if (k->name == name) return k;
+	CUfunction fn = nullptr;
+	if (driver().ModuleGetFunction(&fn, (CUmodule) prg->module, name) != 0) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel '%s' not found in program", name);
+		return NULL;
+	}
+	ccl_kernel* k = new ccl_kernel();
+	k->prg = prg; k->fn = fn; k->name = name;
+	prg->kernels.push_back(k);        /* owned by the program, as in cf4ocl */
+	return k;
+}
+
+extern "C" void ccl_program_destroy(CCLProgram* prg) {
+	if (!prg || !prg->ctx || !clo_handle_alive(prg)) return;
+	clo_handle_remove(prg);
+	for (ccl_kernel* k : prg->kernels) delete k;
+	if (prg->module) {
+		CloDeviceGuard g(prg->ctx->dev.ordinal);
+		driver().ModuleUnload((CUmodule) prg->module);
+	}
+	ccl_context_unref(prg->ctx);
+	delete prg;
+}
+
+namespace {
+std::mutex g_arg_mtx;
+std::vector<ccl_arg*>& live_args() { static std::vector<ccl_arg*> v; return v; }
+
+void set_args_va(ccl_kernel* k, va_list ap) {
+	k->args.clear();
+	for (void* a = va_arg(ap, void*); a; a = va_arg(ap, void*)) {
+		ArgSlot s;
+		if (clo_handle_alive(a)) {                       /* a CCLBuffer: its device address */
+			void* dptr = ((ccl_buffer*) a)->ptr;
+			s.bytes.assign((unsigned char*) &dptr, (unsigned char*) &dptr + sizeof(void*));
+		} else {                                         /* a private value from ccl_arg_priv / ccl_arg_new */
+			std::lock_guard<std::mutex> lk(g_arg_mtx);
+			std::vector<ccl_arg*>& v = live_args();
+			bool found = false;
+			for (size_t i = 0; i < v.size(); ++i) if (v[i] == a) { found = true; v.erase(v.begin() + i); break; }
+			if (!found) continue;
+			s.bytes = ((ccl_arg*) a)->bytes;
+			delete (ccl_arg*) a;
+		}
+		k->args.push_back(s);
+	}
+}
+
+CCLEvent* enqueue(ccl_kernel* k, CCLQueue* cq, cl_uint dims, const size_t* gws, const size_t* lws, GError** err) {
+	if (!k || !cq || dims != 1 || !gws) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "ccl_kernel_enqueue_ndrange: one-dimensional ranges only"); return NULL; }
+	size_t l = (lws && *lws) ? *lws : 0;
+	if (!l) { l = 256; while (l > 1 && (*gws % l)) l >>= 1; }
+	if (*gws % l) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "global work size %zu is not a multiple of the local size %zu", *gws, l); return NULL; }
+	std::vector<void*> ptrs;
+	for (ArgSlot& s : k->args) ptrs.push_back(s.bytes.data());
+	CloDeviceGuard g(cq->ctx->dev.ordinal);
+	ccl_event* evt = clo_queue_begin(cq, k->name.c_str());
+	const int rc = *gws ? driver().LaunchKernel(k->fn, (unsigned) (*gws / l), 1, 1, (unsigned) l, 1, 1, 0, cq->stream, ptrs.data(), nullptr) : 0;
+	clo_queue_end(cq, evt);
+	CLO_COUNT_LAUNCH(1);
+	if (rc != 0) { g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "cuLaunchKernel failed (%d) for '%s'", rc, k->name.c_str()); return NULL; }
+	return evt;
+}
+} // namespace
+
+extern "C" CCLArg* ccl_arg_new(void* value, size_t size) {
+	ccl_arg* a = new ccl_arg();
+	a->magic = 0xC10A26u;
+	a->bytes.assign((unsigned char*) value, (unsigned char*) value + size);
+	std::lock_guard<std::mutex> lk(g_arg_mtx);
+	live_args().push_back(a);
+	return a;
+}
+
+extern "C" void ccl_kernel_set_args(CCLKernel* krnl, ...) {
+	if (!krnl) return;
+	va_list ap;
+	va_start(ap, krnl);
+	set_args_va(krnl, ap);
+	va_end(ap);
+}
+
+extern "C" CCLEvent* ccl_kernel_enqueue_ndrange(CCLKernel* krnl, CCLQueue* cq, cl_uint work_dim, const size_t* gwo,
+		const size_t* gws, const size_t* lws, CCLEventWaitList* ewl, GError** err) {
+	(void) gwo;
+	if (ewl) ccl_event_wait_list_clear(ewl);      /* same-queue ordering is implied by the stream */
+	return enqueue(krnl, cq, work_dim, gws, lws, err);
+}
+
+extern "C" CCLEvent* ccl_kernel_set_args_and_enqueue_ndrange(CCLKernel* krnl, CCLQueue* cq, cl_uint work_dim,
+		const size_t* gwo, const size_t* gws, const size_t* lws, CCLEventWaitList* ewl, GError** err, ...) {
+	(void) gwo;
+	if (!krnl) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "NULL kernel"); return NULL; }
+	va_list ap;
+	va_start(ap, err);
+	set_args_va(krnl, ap);
+	va_end(ap);
+	if (ewl) ccl_event_wait_list_clear(ewl);
+	return enqueue(krnl, cq, work_dim, gws, lws, err);
+}
+
+/* lws in: the caller's maximum (0 = none); out: a power of two <= 256.  With gws == NULL the
+ * local size is made a divisor of real_ws, otherwise gws = real_ws rounded up to it. */
+extern "C" cl_bool ccl_kernel_suggest_worksizes(CCLKernel* krnl, CCLDevice* dev, cl_uint dims, const size_t* real_ws,
+		size_t* gws, size_t* lws, GError** err) {
+	(void) krnl; (void) dev;
+	if (dims != 1 || !real_ws || !lws) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "ccl_kernel_suggest_worksizes: one dimension only"); return CL_FALSE; }
+	size_t cap = (*lws && *lws < 256) ? *lws : 256;
+	size_t l = 1;
+	while (l * 2 <= cap) l *= 2;
+	while (l > 1 && l > *real_ws) l >>= 1;
+	if (gws) {
+		*gws = (*real_ws + l - 1) / l * l;
+	} else {
+		while (l > 1 && (*real_ws % l)) l >>= 1;
+	}
+	*lws = l;
+	return CL_TRUE;
 }

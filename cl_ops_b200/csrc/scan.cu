@@ -506,7 +506,7 @@ struct clo_scan {
 	ReduceFn rfn;
 };
 
-static ccl_program g_scan_program = { "clo_scan (precompiled sm_100a)" };
+static ccl_program g_scan_program = { "clo_scan (precompiled sm_100a)", nullptr, std::string(), nullptr, {} };
 
 static const char* blelloch_init(CloScan* scanner, const char* options, GError** err) {
 	(void) scanner;

@@ -27,7 +27,7 @@ struct clo_sort {
 	CloJitSort* jit;         /* run-time compiled network for compare / get_key strings outside the menu */
 };
 
-static ccl_program g_sort_program = { "clo_sort (precompiled sm_100a)" };
+static ccl_program g_sort_program = { "clo_sort (precompiled sm_100a)", nullptr, std::string(), nullptr, {} };
 
 /* ------------------------------------------------ macro-string "compilation" */
 

@@ -134,6 +134,25 @@ cl_ulong ccl_prof_get_duration(CCLProf* prof);
 /* ---- leak check: true iff no shim handle is alive ---- */
 cl_bool ccl_wrapper_memcheck(void);
 
+
+/* programs and kernels built from source at run time (NVRTC): what clo_rng_bench.c:176-312 and
+ * tests/test_rng.c:85-118 do with clo_rng_get_source() */
+typedef struct ccl_kernel CCLKernel;
+typedef struct ccl_arg CCLArg;
+CCLProgram* ccl_program_new_from_source(CCLContext* ctx, const char* src, GError** err);
+cl_bool ccl_program_build(CCLProgram* prg, const char* options, GError** err);
+CCLKernel* ccl_program_get_kernel(CCLProgram* prg, const char* kernel_name, GError** err);
+void ccl_program_destroy(CCLProgram* prg);
+CCLArg* ccl_arg_new(void* value, size_t size);
+#define ccl_arg_priv(value, type) ccl_arg_new(&value, sizeof(type))
+void ccl_kernel_set_args(CCLKernel* krnl, ...);
+CCLEvent* ccl_kernel_enqueue_ndrange(CCLKernel* krnl, CCLQueue* cq, cl_uint work_dim,
+	const size_t* gwo, const size_t* gws, const size_t* lws, CCLEventWaitList* ewl, GError** err);
+CCLEvent* ccl_kernel_set_args_and_enqueue_ndrange(CCLKernel* krnl, CCLQueue* cq, cl_uint work_dim,
+	const size_t* gwo, const size_t* gws, const size_t* lws, CCLEventWaitList* ewl, GError** err, ...);
+cl_bool ccl_kernel_suggest_worksizes(CCLKernel* krnl, CCLDevice* dev, cl_uint dims,
+	const size_t* real_ws, size_t* gws, size_t* lws, GError** err);
+
 /* ---- CUDA-side constructors / accessors (additive; not in cf4ocl2) ---- */
 /* Wrap an existing cudaStream_t (passed as void*; NULL = legacy default stream). */
 CCLQueue* ccl_queue_new_wrap(CCLContext* ctx, void* cuda_stream, GError** err);

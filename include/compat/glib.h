@@ -88,6 +88,8 @@ gboolean g_str_has_prefix(const gchar* s, const gchar* prefix);
 gint g_ascii_strncasecmp(const gchar* a, const gchar* b, gsize n);
 gpointer g_slice_alloc(gsize n);
 void g_slice_free1(gsize n, gpointer p);
+typedef void (*GPrintFunc)(const gchar* string);
+GPrintFunc g_set_print_handler(GPrintFunc func);     /* g_print goes through the handler when one is set */
 void g_print(const gchar* format, ...);
 void clo_b200_g_debug(const gchar* format, ...);      /* printed when G_MESSAGES_DEBUG is set */
 void clo_b200_g_assert_fail(const char* expr, const char* loc);
@@ -108,6 +110,12 @@ gint32 g_rand_int_range(GRand* r, gint32 begin, gint32 end);
 gdouble g_rand_double(GRand* r);
 gdouble g_rand_double_range(GRand* r, gdouble begin, gdouble end);
 #define g_rand_boolean(r) ((g_rand_int(r) & (1 << 15)) != 0)
+
+/* GLib's test harness, as far as src/tests/test_rng.c:444-462 uses it */
+typedef void (*GTestFunc)(void);
+void g_test_init(int* argc, char*** argv, ...);
+void g_test_add_func(const char* testpath, GTestFunc test_func);
+int g_test_run(void);
 
 typedef struct _GTimer GTimer;
 GTimer* g_timer_new(void);

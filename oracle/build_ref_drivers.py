@@ -32,13 +32,32 @@ def main():
         o = os.path.join(OUT, name + ".o")
         subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-w"] + inc + ["-c", os.path.join(bench, name + ".c"), "-o", o])
         objs[name] = o
-    for exe in ("clo_sort_bench", "clo_scan_bench"):
+    # clo_rng_bench: its header is a CMake template holding the bench kernel as a C string
+    # (clo_rng_bench.in.h: CLO_RNG_BENCHMARK_SRC "@RNG_BENCHMARK_SRC@"); do CMake's configure step
+    # here, into the build directory, from the .cl where it lies
+    gen = os.path.join(OUT, "gen")
+    os.makedirs(gen, exist_ok=True)
+    cl = open(os.path.join(bench, "clo_rng_bench.cl")).read()
+    esc = cl.replace("\\", "\\\\").replace('"', '\\"').replace("\n", "\\n\" \\\n\"")
+    tmpl = open(os.path.join(bench, "clo_rng_bench.in.h")).read()
+    with open(os.path.join(gen, "clo_rng_bench.h"), "w") as f:
+        f.write(tmpl.replace("@RNG_BENCHMARK_SRC@", esc))
+    o = os.path.join(OUT, "clo_rng_bench.o")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-w", "-I" + gen] + inc + ["-c", os.path.join(bench, "clo_rng_bench.c"), "-o", o])
+    objs["clo_rng_bench"] = o
+    # the reference's only unit test
+    o = os.path.join(OUT, "test_rng.o")
+    subprocess.check_call(["gcc", "-std=gnu99", "-O2", "-w"] + inc + ["-c", os.path.join(REF, "src", "tests", "test_rng.c"), "-o", o])
+    subprocess.check_call(["gcc", "-o", os.path.join(OUT, "test_rng"), o, "-L" + os.path.join(ROOT, "cl_ops_b200"), "-lcl_ops", "-lm",
+                           "-Wl,-rpath,$ORIGIN/../../cl_ops_b200"])
+    os.remove(o)
+    for exe in ("clo_sort_bench", "clo_scan_bench", "clo_rng_bench"):
         subprocess.check_call(["gcc", "-o", os.path.join(OUT, exe), objs[exe], objs["clo_bench"],
                                "-L" + os.path.join(ROOT, "cl_ops_b200"), "-lcl_ops", "-lm",
                                "-Wl,-rpath,$ORIGIN/../../cl_ops_b200"])
     for o in objs.values():
         os.remove(o)
-    print("build_ref_drivers: wrote %s/{clo_sort_bench,clo_scan_bench}" % OUT)
+    print("build_ref_drivers: wrote %s/{clo_sort_bench,clo_scan_bench,clo_rng_bench,test_rng}" % OUT)
     return 0
 
 

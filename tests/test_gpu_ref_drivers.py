@@ -38,3 +38,46 @@ def test_reference_scan_bench_unchanged(typ, sumtyp):
     assert len(lines) > 0
     for l in lines:
         assert "did not work" not in l and "Unverified" not in l
+
+
+def test_reference_test_rng_unchanged():
+    """src/tests/test_rng.c, the reference's only unit test: for every generator and every seeding
+    mode it concatenates clo_rng_get_source() with an OpenCL C kernel, builds it (here: NVRTC),
+    runs it and asserts no error and no leaked wrapper."""
+    out = _run("test_rng")
+    for path in ("/rng/seed-dev-gid", "/rng/seed-host-mt", "/rng/seed-ext-dev", "/rng/seed-ext-host"):
+        assert path + ": OK" in out
+
+
+@pytest.mark.parametrize("rng", ["lcg", "xorshift64", "xorshift128", "mwc64x", "parkmiller", "tauslcg"])
+@pytest.mark.parametrize("hash_", ["KNUTH(x)", "XS1(x)"])
+def test_reference_rng_bench_unchanged_stream_is_bit_exact(rng, hash_):
+    """src/benchmarks/clo_rng_bench.c with --output stdout-uint: the numbers its own kernel
+    (clo_rng_bench.cl, built at run time on top of clo_rng_get_source()) prints are the oracle's
+    stream, run after run."""
+    import numpy as np
+    import oracle
+    G, runs, seed = 2048, 5, 77
+    out = _run("clo_rng_bench", "-r", rng, "-o", "stdout-uint", "-g", str(G), "-n", str(runs), "-s", str(seed),
+               "--gid-hash", hash_, "-b", "32")
+    got = np.array([int(t) for t in out.split()], dtype=np.uint64).astype(np.uint32)
+    seeds = oracle.rng_seeds_dev_gid(rng, oracle.HASH_IDS[hash_], seed, G)
+    want, _ = oracle.rng_generate(rng, seeds, G, runs)
+    assert got.size == G * runs
+    assert np.array_equal(got, want.reshape(-1))
+
+
+def test_reference_rng_bench_unchanged_maxint_and_bits():
+    import numpy as np
+    import oracle
+    G, runs = 1024, 3
+    out = _run("clo_rng_bench", "-r", "mwc64x", "-o", "stdout-uint", "-g", str(G), "-n", str(runs), "-s", "5", "--gid-hash", "KNUTH(x)", "-m", "1000")
+    got = np.array([int(t) for t in out.split()], dtype=np.uint32)
+    seeds = oracle.rng_seeds_dev_gid("mwc64x", 1, 5, G)
+    want, _ = oracle.rng_generate("mwc64x", seeds, G, runs, maxint=1000)
+    assert np.array_equal(got, want.reshape(-1))
+    out = _run("clo_rng_bench", "-r", "xorshift64", "-o", "stdout-uint", "-g", str(G), "-n", str(runs), "-s", "5", "--gid-hash", "KNUTH(x)", "-b", "8")
+    got = np.array([int(t) for t in out.split()], dtype=np.uint32)
+    seeds = oracle.rng_seeds_dev_gid("xorshift64", 1, 5, G)
+    want, _ = oracle.rng_generate("xorshift64", seeds, G, runs, bits=8)
+    assert np.array_equal(got, want.reshape(-1))
