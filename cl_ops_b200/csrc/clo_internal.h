@@ -132,4 +132,8 @@ cudaError_t clo_partition_scatter_stage(CloScratch& work, size_t elem_size, cons
 		const uint64_t* first_slot, void* const* dests, void* const* vdests, const int* ok, int sm_count,
 		cudaStream_t stream, const char** err_msg);
 
+/* hashed 64-bit seeds for a CLO_RNG_HASH string outside the menu, built with NVRTC (jit.cu) */
+cudaError_t clo_jit_seed_hash(const char* hash, unsigned long long* seeds_dev, size_t count, unsigned long long gid0,
+		unsigned long long main_seed, cudaStream_t stream, std::string& msg);
+
 #endif

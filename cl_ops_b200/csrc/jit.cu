@@ -488,3 +488,84 @@ extern "C" cl_bool ccl_kernel_suggest_worksizes(CCLKernel* krnl, CCLDevice* dev,
 	*lws = l;
 	return CL_TRUE;
 }
+
+/* =====================================================================================
+ * Seed hashes outside the menu: the reference defines CLO_RNG_HASH(x) as the caller's string
+ * and builds it into its init kernel (clo_rng.c:101-109, clo_rng_init.cl:27-60).  Here the
+ * string is built, once per distinct string, into a kernel that produces the hashed 64-bit
+ * seeds; rng.cu turns them into generator states (clo_ulong2statetype).
+ * ===================================================================================== */
+namespace {
+const char kHashBody[] = R"SRC(
+typedef unsigned char uchar;
+typedef unsigned short ushort;
+typedef unsigned int uint;
+typedef unsigned long long ulong;
+#define KNUTH(x) x = ((x*2654435761) % 0x100000000)
+#define XS1(x) \
+	x = ((x >> 16) ^ x) * 0x45d9f3b; \
+	x = ((x >> 16) ^ x) * 0x45d9f3b; \
+	x = ((x >> 16) ^ x);
+extern "C" __global__ void clo_jit_seed_hash(ulong* seeds, ulong count, ulong gid0, ulong main_seed) {
+	const ulong i = (ulong) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	ulong seed = gid0 + i + main_seed;
+	CLO_RNG_HASH(seed);
+	seeds[i] = seed;
+}
+)SRC";
+
+struct HashModule { CUmodule mod; CUfunction fn; };
+std::mutex g_hash_mtx;
+std::vector<std::pair<std::string, HashModule>>& hash_cache() { static std::vector<std::pair<std::string, HashModule>> v; return v; }
+} // namespace
+
+cudaError_t clo_jit_seed_hash(const char* hash, unsigned long long* seeds_dev, size_t count, unsigned long long gid0,
+		unsigned long long main_seed, cudaStream_t stream, std::string& msg) {
+	Nvrtc& rt = nvrtc();
+	Driver& drv = driver();
+	if (!rt.ok || !drv.ok) { msg = "a custom seed hash needs NVRTC and the CUDA driver"; return cudaErrorNotSupported; }
+	HashModule hm = { nullptr, nullptr };
+	{
+		std::lock_guard<std::mutex> lk(g_hash_mtx);
+		for (auto& e : hash_cache()) if (e.first == hash) hm = e.second;
+	}
+	if (!hm.fn) {
+		std::string src = "#define CLO_RNG_HASH(x) ";
+		src += hash; src += "\n"; src += kHashBody;
+		nvrtcProgram np = nullptr;
+		if (rt.CreateProgram(&np, src.c_str(), "clo_rng_hash.cu", 0, nullptr, nullptr) != 0) { msg = "nvrtcCreateProgram failed"; return cudaErrorUnknown; }
+		const char* opts[] = { "--gpu-architecture=sm_100a", "--std=c++17", "-default-device" };
+		if (rt.CompileProgram(np, 3, opts) != 0) {
+			size_t ls = 0;
+			rt.GetProgramLogSize(np, &ls);
+			std::vector<char> log(ls + 1, 0);
+			if (ls) rt.GetProgramLog(np, log.data());
+			msg = "the seed hash does not compile: ";
+			msg += log.data();
+			rt.DestroyProgram(&np);
+			return cudaErrorInvalidValue;
+		}
+		size_t cs = 0;
+		rt.GetCUBINSize(np, &cs);
+		std::vector<char> cubin(cs);
+		rt.GetCUBIN(np, cubin.data());
+		rt.DestroyProgram(&np);
+		cudaFree(0);
+		if (drv.ModuleLoadData(&hm.mod, cubin.data()) != 0 || drv.ModuleGetFunction(&hm.fn, hm.mod, "clo_jit_seed_hash") != 0) {
+			msg = "loading the seed-hash module failed";
+			return cudaErrorUnknown;
+		}
+		std::lock_guard<std::mutex> lk(g_hash_mtx);
+		hash_cache().push_back({ hash, hm });
+	}
+	if (!count) return cudaSuccess;
+	unsigned long long c = count;
+	void* args[] = { &seeds_dev, &c, &gid0, &main_seed };
+	if (drv.LaunchKernel(hm.fn, (unsigned) ((count + 255) / 256), 1, 1, 256, 1, 1, 0, stream, args, nullptr) != 0) {
+		msg = "launching the seed-hash kernel failed";
+		return cudaErrorLaunchFailure;
+	}
+	CLO_COUNT_LAUNCH(1);
+	return cudaSuccess;
+}

@@ -13,6 +13,8 @@
  * HBM traffic: 4 bytes per generated word (+ 2 * seed_size per stream per call).
  */
 #include "clo_internal.h"
+#include <string>
+#include <cctype>
 #include "device_utils.cuh"
 
 #include <cstring>
@@ -138,6 +140,14 @@ __global__ void clo_rng_init_kernel(typename Gen<R>::State* __restrict__ states,
 	states[i] = Gen<R>::from_seed(seed);
 }
 
+/* states from already hashed 64-bit seeds (custom CLO_RNG_HASH strings, built by jit.cu) */
+template <int R>
+__global__ void clo_rng_init_from_seeds_kernel(typename Gen<R>::State* __restrict__ states, size_t count,
+		const u64* __restrict__ seeds) {
+	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < count) states[i] = Gen<R>::from_seed(seeds[i]);
+}
+
 /* Bulk generation, layout of clo_rng_bench.cl:23-37 + clo_rng_bench.c:302-324:
  * out[r * G + g] = f(next_r(state_g)), f = >> shift  or  % maxint. */
 template <int R>
@@ -212,9 +222,20 @@ cudaError_t launch_generate(void* states, size_t G, size_t runs, void* out, u32 
 }
 
 typedef cudaError_t (*InitFn)(void*, size_t, u64, u64, int, cudaStream_t);
+template <int R>
+cudaError_t launch_init_from_seeds(void* states, size_t count, const u64* seeds, cudaStream_t stream) {
+	if (!count) return cudaSuccess;
+	clo_rng_init_from_seeds_kernel<R><<<(unsigned) ((count + 255) / 256), 256, 0, stream>>>((typename Gen<R>::State*) states, count, seeds);
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
+}
+typedef cudaError_t (*InitSeedsFn)(void*, size_t, const u64*, cudaStream_t);
+
 typedef cudaError_t (*GenFn)(void*, size_t, size_t, void*, u32, u32, cudaStream_t);
 
 const InitFn kInit[R_COUNT] = { launch_init<0>, launch_init<1>, launch_init<2>, launch_init<3>, launch_init<4>, launch_init<5> };
+const InitSeedsFn kInitSeeds[R_COUNT] = { launch_init_from_seeds<0>, launch_init_from_seeds<1>, launch_init_from_seeds<2>,
+	launch_init_from_seeds<3>, launch_init_from_seeds<4>, launch_init_from_seeds<5> };
 const GenFn kGen[R_COUNT] = { launch_generate<0>, launch_generate<1>, launch_generate<2>, launch_generate<3>, launch_generate<4>, launch_generate<5> };
 
 /* ------------------------------------------------------------- sources */
@@ -336,20 +357,21 @@ struct HostMT {
 	}
 };
 
+const int H_CUSTOM = 100;     /* any other string: built at run time (jit.cu), as the reference builds it */
+
 int parse_hash(const char* hash, GError** err) {
+	(void) err;
 	if (!hash || !*hash || strcmp(hash, "x") == 0) return H_NONE;
-	if (strstr(hash, "KNUTH")) return H_KNUTH;
-	if (strstr(hash, "XS1")) return H_XS1;
+	std::string sq;
+	for (const char* p = hash; *p; ++p) if (!isspace((unsigned char) *p)) sq.push_back(*p);
+	if (sq == "KNUTH(x)" || sq == "KNUTH(x);") return H_KNUTH;
+	if (sq == "XS1(x)" || sq == "XS1(x);") return H_XS1;
 	/* an expression that does not assign to x is a no-op statement in the
 	 * reference's `CLO_RNG_HASH(seed);` (clo_rng_init.cl:55), e.g. test_rng.c:42 */
-	for (const char* p = hash; *p; ++p) {
-		if (*p == '=' && p[1] != '=' && (p == hash || (p[-1] != '=' && p[-1] != '!' && p[-1] != '<' && p[-1] != '>'))) {
-			g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS,
-				"Seed hash '%s' is not one of the supported hashes (KNUTH(x), XS1(x), none)", hash);
-			return -1;
-		}
-	}
-	return H_NONE;
+	bool assigns = strstr(hash, "KNUTH") || strstr(hash, "XS1") || strstr(hash, "++") || strstr(hash, "--");
+	for (const char* p = hash; *p; ++p)
+		if (*p == '=' && p[1] != '=' && (p == hash || (p[-1] != '=' && p[-1] != '!' && p[-1] != '<' && p[-1] != '>'))) assigns = true;
+	return assigns ? H_CUSTOM : H_NONE;
 }
 
 CloRng* rng_new_impl(const char* type, CloRngSeedType seed_type, void* seeds, size_t seeds_count,
@@ -385,6 +407,16 @@ CloRng* rng_new_impl(const char* type, CloRngSeedType seed_type, void* seeds, si
 		dev_seeds = ccl_buffer_new(ctx, CL_MEM_READ_WRITE, bytes, NULL, &ierr);
 		if (ierr) break;
 		CloDeviceGuard g(ctx->dev.ordinal);
+		if (h == H_CUSTOM) {
+			void* tmp = NULL;
+			std::string msg;
+			if (clo_cuda_failed(cudaMallocAsync(&tmp, seeds_count ? seeds_count * 8 : 8, cq->stream), &ierr, "cudaMallocAsync")) break;
+			cudaError_t rc = clo_jit_seed_hash(hash, (unsigned long long*) tmp, seeds_count, gid_offset, main_seed, cq->stream, msg);
+			if (rc != cudaSuccess) g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg.c_str());
+			else clo_cuda_failed(kInitSeeds[id](dev_seeds->ptr, seeds_count, (const u64*) tmp, cq->stream), &ierr, "clo_rng_init");
+			cudaFreeAsync(tmp, cq->stream);
+			break;
+		}
 		clo_cuda_failed(kInit[id](dev_seeds->ptr, seeds_count, gid_offset, main_seed, h, cq->stream), &ierr, "clo_rng_init");
 		break; }
 	case CLO_RNG_SEED_HOST_MT: {

@@ -90,3 +90,27 @@ def test_rng_errors_and_source(clo, ctx, queue):
     assert "clo_rng_next" in r.get_source()
     assert np.array_equal(r.read_seeds(queue), oracle.rng_seeds_dev_gid("mwc64x", 0, 0, 16))
     r.destroy()
+
+
+def test_custom_seed_hash_strings_are_compiled_at_run_time(clo, ctx, queue):
+    """CLO_RNG_HASH strings outside {none, KNUTH(x), XS1(x)} are built into the seeding kernel at
+    run time (clo_rng.c:101-109 does the same with its OpenCL program): checked against the
+    formula in 64-bit arithmetic and clo_ulong2statetype of lcg / xorshift128."""
+    G, ms = 5000, 99
+    gid = np.arange(G, dtype=np.uint64) + np.uint64(ms)
+    with np.errstate(over="ignore"):
+        want1 = gid * np.uint64(3) + np.uint64(1)
+        want2 = ((gid * np.uint64(2654435761)) % np.uint64(1 << 32)) ^ np.uint64(0xABCDEF)
+    r = clo.CloRng("lcg", ctx, clo.SEED_DEV_GID, None, G, ms, "x = x * 3 + 1", queue)
+    assert np.array_equal(r.read_seeds(queue).view(np.uint64), want1)
+    r.destroy()
+    r = clo.CloRng("xorshift128", ctx, clo.SEED_DEV_GID, None, G, ms, "KNUTH(x); x ^= 0xABCDEF", queue)
+    st = r.read_seeds(queue).view(np.uint32).reshape(G, 4)
+    s = want2
+    exp = np.stack([s & 0xFFFFFFFF, (s >> np.uint64(16)) & 0xFFFFFFFF, (s >> np.uint64(32)) & 0xFFFFFFFF,
+                    (s >> np.uint64(46)) & 0xFFFFFFFF], axis=1).astype(np.uint32)
+    assert np.array_equal(st, exp)
+    r.destroy()
+    with pytest.raises(clo.CloError) as ei:
+        clo.CloRng("lcg", ctx, clo.SEED_DEV_GID, None, 16, 0, "x = x +* 2", queue)
+    assert ei.value.code == clo.CLO_ERROR_ARGS and "does not compile" in str(ei.value)
