@@ -99,17 +99,44 @@ clo_partition_count(const ElemT* __restrict__ in, size_t n, size_t chunk, u32 to
 	__syncwarp();
 	const size_t lo = (size_t) w * chunk;
 	const size_t hi = lo + chunk < n ? lo + chunk : n;
-	for (size_t base = lo; base < hi; base += 32 * PT_U) {
-		ElemT k[PT_U];
+	/* counting does not care about the order inside the chunk: 16-byte loads, 4 of them in flight */
+	constexpr int EPV = 16 / (int) sizeof(ElemT);
+	constexpr int VU = 4;
+	const bool vec_ok = (reinterpret_cast<uintptr_t>(in) % 16) == 0;
+	if (vec_ok) {
+		for (size_t base = lo; base < hi; base += (size_t) 32 * EPV * VU) {
+			ElemT k[VU][EPV];
 #pragma unroll
-		for (int u = 0; u < PT_U; ++u) {
-			const size_t i = base + u * 32 + lane;
-			k[u] = i < hi ? __ldcs(in + i) : ElemT(0);
+			for (int u = 0; u < VU; ++u) {
+				const size_t i0 = base + ((size_t) u * 32 + lane) * EPV;
+				if (i0 + EPV <= hi) {
+					load_vec_cs<ElemT, EPV>(in + i0, k[u]);
+				} else {
+#pragma unroll
+					for (int c = 0; c < EPV; ++c) k[u][c] = (i0 + c < hi) ? __ldcs(in + i0 + c) : ElemT(0);
+				}
+			}
+#pragma unroll
+			for (int u = 0; u < VU; ++u)
+#pragma unroll
+				for (int c = 0; c < EPV; ++c) {
+					const size_t i = base + ((size_t) u * 32 + lane) * EPV + c;
+					if (i < hi) atomicAdd(&sh[warp][pt_bucket<ElemT, NS>(k[u][c], sp.gidx0 + i, sp)], 1u);
+				}
 		}
+	} else {
+		for (size_t base = lo; base < hi; base += 32 * PT_U) {
+			ElemT k[PT_U];
 #pragma unroll
-		for (int u = 0; u < PT_U; ++u) {
-			const size_t i = base + u * 32 + lane;
-			if (i < hi) atomicAdd(&sh[warp][pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp)], 1u);
+			for (int u = 0; u < PT_U; ++u) {
+				const size_t i = base + u * 32 + lane;
+				k[u] = i < hi ? __ldcs(in + i) : ElemT(0);
+			}
+#pragma unroll
+			for (int u = 0; u < PT_U; ++u) {
+				const size_t i = base + u * 32 + lane;
+				if (i < hi) atomicAdd(&sh[warp][pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp)], 1u);
+			}
 		}
 	}
 	__syncwarp();
