@@ -26,6 +26,17 @@
  *              (slow, self-contained, never seen on B200; forced by flag 8 in the tests).
  * The staging buffers alternate, so a tile's write-out is separated from its staging by the
  * two barriers of the following iteration and needs none of its own.
+ *
+ * Round 2 (ncu: the pass is bound by the shared-memory data pipe, 19 wavefronts per 32 keys):
+ *   - the warp histograms are PACKED, two 16-bit digit counters per word (a staged tile has
+ *     < 2^16 slots): 128 digit threads own two digits each, so the digit phase and the row
+ *     clearing touch half the words;
+ *   - VERIFY is a template flag.  The per-tile stability check costs one more LDS per key; the
+ *     launcher runs clo_radix_atomic_order_selftest ONCE per device (the same instruction
+ *     forms on heavily colliding addresses, checked against __match_any_sync ranks) and uses
+ *     the unverified instance only when the device serves same-address lanes in lane order.
+ *     CLO_RADIX_VERIFY=1 forces the verified instance; flag 16 plants a real inversion in
+ *     front of the detector (tests).
  */
 #ifndef CLO_RADIX_V6_CUH
 #define CLO_RADIX_V6_CUH
@@ -99,7 +110,7 @@ __device__ __noinline__ void v6_repair(const ElemT* __restrict__ in, ElemT* __re
 __host__ __device__ constexpr int v6_prop_groups(int threads, int word_bytes) { return (threads >= 512 && word_bytes == 4) ? 2 : 1; }
 __host__ __device__ constexpr int v6_num_prop(int threads, int word_bytes) { return RADIX / 32 / v6_prop_groups(threads, word_bytes); }
 
-template <typename ElemT, typename LbT, int THREADS, int IPT, bool HAS_VAL = false>
+template <typename ElemT, typename LbT, int THREADS, int IPT, bool HAS_VAL = false, bool VERIFY = true>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 3 : 2))
 clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n, u32 num_tiles,
@@ -109,11 +120,14 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	constexpr int WARPS = THREADS / 32;
 	constexpr int TILE = THREADS * IPT;
 	constexpr u32 NONE = 0xffffffffu;
-	static_assert(THREADS > RADIX && RADIX % (THREADS - RADIX) == 0, "256 digit threads + prefix threads owning whole digits");
-	constexpr int PREF_T = THREADS - RADIX;        /* prefix threads */
+	constexpr int DT = RADIX / 2;                  /* digit threads: two digits (one packed word) each */
+	constexpr int ROWW = RADIX / 2;                /* packed words per warp row */
+	constexpr int PREF_T = (THREADS - DT) >= RADIX ? RADIX : (THREADS - DT);   /* prefix threads: tid in [DT, DT + PREF_T) */
+	static_assert(THREADS > DT && RADIX % PREF_T == 0, "128 digit threads + prefix threads owning whole digits");
 	constexpr int DPT = RADIX / PREF_T;            /* digits per prefix thread */
+	static_assert(ROWW == 128, "a lane clears its share of a row with one 16-byte store");
 	static_assert((size_t) TILE * sizeof(ElemT) >= (size_t) WARPS * RADIX * 4, "repair scratch lives in a staging buffer");
-	static_assert(TILE <= 65536, "index in tile must fit 16 bits");
+	static_assert(TILE < 65536, "slots and indices in a tile must fit 16 bits");
 
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -132,18 +146,22 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		if (s_trivial) {
 			constexpr int NP = v6_num_prop(THREADS, (int) sizeof(LbT));
 			if (blockIdx.x < NP) return;
-			const u32 wb = (u32) (threadIdx.x >> 5) * 32u * IPT + (threadIdx.x & 31);
-			for (u32 t = blockIdx.x - NP; t < num_tiles; t += gridDim.x - NP) {
-				const size_t base = (size_t) t * TILE;
-#pragma unroll
-				for (int i = 0; i < IPT; ++i) {
-					const size_t j = base + wb + i * 32u;
-					if (j < n) {
-						out[j] = __ldcs(in + j);
-						if (HAS_VAL) vout[j] = __ldcs(vin + j);
-					}
+			/* 16 bytes per thread and step when the buffers allow it (cudaMalloc'ed ones always do) */
+			auto copy = [&](const void* src, void* dst, size_t bytes) {
+				const size_t w = (size_t) (blockIdx.x - NP) * THREADS + threadIdx.x, stride = (size_t) (gridDim.x - NP) * THREADS;
+				if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0) {
+					const size_t nv = bytes / 16;
+					for (size_t i = w; i < nv; i += stride)
+						__stcs(reinterpret_cast<uint4*>(dst) + i, __ldcs(reinterpret_cast<const uint4*>(src) + i));
+					for (size_t i = nv * 16 + w; i < bytes; i += stride)
+						reinterpret_cast<unsigned char*>(dst)[i] = reinterpret_cast<const unsigned char*>(src)[i];
+				} else {
+					for (size_t i = w; i < bytes / 4; i += stride)
+						reinterpret_cast<u32*>(dst)[i] = __ldcs(reinterpret_cast<const u32*>(src) + i);
 				}
-			}
+			};
+			copy(in, out, n * sizeof(ElemT));
+			if (HAS_VAL) copy(vin, vout, n * 4);
 			return;
 		}
 	}
@@ -177,8 +195,8 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		if (s_leave) return;
 	}
 
-	u32* whist = reinterpret_cast<u32*>(smem_raw);                          /* [WARPS][RADIX] */
-	u32* s_ds = whist + WARPS * RADIX;                                      /* [2][RADIX] digit starts */
+	u32* whist = reinterpret_cast<u32*>(smem_raw);                          /* [WARPS][ROWW] packed: digit d = half (d & 1) of word d >> 1 */
+	u32* s_ds = whist + WARPS * ROWW;                                       /* [3][RADIX] digit starts (+1 pad) */
 	u64* s_goff_raw = reinterpret_cast<u64*>(s_ds + 4 * RADIX);             /* [2][RADIX] u64-sized slots (s_ds has 3 live slots + 1 pad) */
 	u32* s_misc = reinterpret_cast<u32*>(s_goff_raw + 2 * RADIX);           /* [16]: 0..7 scan, 8 ticket, 10..11 bad */
 	/* staging, per buffer: keys [TILE]; with a payload also values [TILE] and the index in tile
@@ -192,11 +210,12 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 	const ElemT low_mask = (ElemT) ((((ElemT) dmask) << start_bit) | ((((ElemT) 1) << start_bit) - 1));
 	const u32 wbase = (u32) warp * 32u * IPT + lane;
-	u32* wh = whist + warp * RADIX;
-	/* the prefix threads own one digit each */
+	u32* wh = whist + warp * ROWW;
+	/* the prefix threads own DPT digits each */
+	const bool is_pref_thread = tid >= DT && tid < DT + PREF_T;
 	LbT my_base[DPT];
 #pragma unroll
-	for (int j = 0; j < DPT; ++j) my_base[j] = tid >= RADIX ? (LbT) bins_base[tid - RADIX + j * PREF_T] : (LbT) 0;
+	for (int j = 0; j < DPT; ++j) my_base[j] = is_pref_thread ? (LbT) bins_base[tid - DT + j * PREF_T] : (LbT) 0;
 
 	ElemT key[IPT];
 	u32 val[HAS_VAL ? IPT : 1];
@@ -238,25 +257,52 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			}
 		}
 	};
-	auto zero_row = [&]() {
-		uint4* row = reinterpret_cast<uint4*>(wh);
-#pragma unroll
-		for (int i = 0; i < RADIX / 4 / 32; ++i) row[lane + i * 32] = make_uint4(0u, 0u, 0u, 0u);
+	auto zero_row = [&]() { reinterpret_cast<uint4*>(wh)[lane] = make_uint4(0u, 0u, 0u, 0u); };
+	/* +1 on digit d's packed counter; the returning form gives the counter's old value */
+	auto row_count = [&](u32 d) { atomicAdd(&wh[d >> 1], 1u << ((d & 1u) << 4)); };
+	auto row_take = [&](u32 d) -> u32 {
+		const u32 sh = (d & 1u) << 4;
+		return (atomicAdd(&wh[d >> 1], 1u << sh) >> sh) & 0xffffu;
 	};
 	/* coalesced write-out of a staged tile; returns true when the staged order is not
 	 * sorted on the bits processed so far (= some warp instruction's atomics were not
 	 * applied in lane order) */
-	auto write_out = [&](u32 t, int b, int gslot, bool verify) -> bool {
+	/* executed by the threads [first, first + nthr) of the CTA (nthr a multiple of 32); bar_id names
+	 * the barrier those threads share (0 = the whole CTA) */
+	auto write_out = [&](u32 t, int b, int gslot, bool verify, const int first, const int nthr, const int bar_id) -> bool {
 		const u32 cnt = tile_count_of(t);
+		const u32 lid = (u32) (tid - first);
 		const ElemT* skeys = buf_keys(b);
 		const u32* svals = buf_vals(b);
 		const unsigned short* sinfo = buf_info(b);
 		const LbT* goff = goff_of(gslot);
 		bool bad = false;
+		if (flags & 16) {
+			/* test hook: plant a REAL inversion -- swap two neighbouring staged entries of the same
+			 * digit -- before the detector looks, so the predicate itself is exercised */
+			if (lid == 0 && (t % 7u) == 3u) {
+				ElemT* wk = const_cast<ElemT*>(skeys);
+				u32* wv = const_cast<u32*>(svals);
+				unsigned short* wi = const_cast<unsigned short*>(sinfo);
+				for (u32 j = 1; j < cnt; ++j) {
+					const ElemT a = wk[j - 1], b2 = wk[j];
+					if (v6_digit<ElemT>(a, start_bit, dmask) != v6_digit<ElemT>(b2, start_bit, dmask)) continue;
+					if (!HAS_VAL && (a & low_mask) == (b2 & low_mask)) continue;
+					wk[j - 1] = b2; wk[j] = a;
+					if (HAS_VAL) {
+						const u32 v = wv[j - 1]; wv[j - 1] = wv[j]; wv[j] = v;
+						const unsigned short x = wi[j - 1]; wi[j - 1] = wi[j]; wi[j] = x;
+					}
+					atomicAdd(err_flag + 2, 1);
+					break;
+				}
+			}
+			named_bar_sync(bar_id, nthr);
+		}
 		if ((flags & 8) && (t % 5u) == 2u) {
 			/* test hook: write this tile WRONG and report it, so that only a working repair
 			 * path gives a sorted result */
-			for (u32 j = tid; j < cnt; j += THREADS) {
+			for (u32 j = lid; j < cnt; j += (u32) nthr) {
 				const ElemT k = skeys[j];
 				const LbT o = goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j;
 				out[o] = (ElemT) ~k;
@@ -266,25 +312,36 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		}
 		auto one = [&](u32 j) {
 			const ElemT k = skeys[j];
-			const ElemT kp = skeys[j > 0 ? j - 1 : 0];
 			const u32 d = v6_digit<ElemT>(k, start_bit, dmask);
-			if (HAS_VAL) {
-				/* equal digits must keep their order in the tile (payloads tell equal keys apart) */
-				if (j > 0 && v6_digit<ElemT>(kp, start_bit, dmask) == d && sinfo[j] <= sinfo[j - 1]) bad = true;
-			} else {
-				if ((k & low_mask) < (kp & low_mask)) bad = true;
+			if (VERIFY) {
+				const ElemT kp = skeys[j > 0 ? j - 1 : 0];
+				if (HAS_VAL) {
+					/* equal digits must keep their order in the tile (payloads tell equal keys apart) */
+					if (j > 0 && v6_digit<ElemT>(kp, start_bit, dmask) == d && sinfo[j] <= sinfo[j - 1]) bad = true;
+				} else {
+					if ((k & low_mask) < (kp & low_mask)) bad = true;
+				}
 			}
 			const LbT o = goff[d] + (LbT) j;
 			out[o] = k;
 			if (HAS_VAL) vout[o] = svals[j];
 		};
-		if (cnt == (u32) TILE) {
+		if (nthr == THREADS) {
+			if (cnt == (u32) TILE) {
 #pragma unroll
-			for (int i = 0; i < IPT; ++i) one((u32) tid + i * THREADS);
+				for (int i = 0; i < IPT; ++i) one(lid + i * THREADS);
+			} else {
+#pragma unroll
+				for (int i = 0; i < IPT; ++i) {
+					const u32 j = lid + i * THREADS;
+					if (j < cnt) one(j);
+				}
+			}
 		} else {
+			constexpr int ROUNDS = (TILE + (THREADS - DT) - 1) / (THREADS - DT);
 #pragma unroll
-			for (int i = 0; i < IPT; ++i) {
-				const u32 j = (u32) tid + i * THREADS;
+			for (int i = 0; i < ROUNDS; ++i) {
+				const u32 j = lid + i * (u32) (THREADS - DT);
 				if (j < cnt) one(j);
 			}
 		}
@@ -294,7 +351,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	auto prefix_to_goff = [&](u32 t, int gslot, int dslot, const LbT (&w0)[DPT]) {
 #pragma unroll
 		for (int j = 0; j < DPT; ++j) {
-			const int d = tid - RADIX + j * PREF_T;
+			const int d = tid - DT + j * PREF_T;
 			LbT* p = pref + (size_t) t * RADIX + d;
 			LbT w = w0[j];
 			unsigned spins = 0;
@@ -312,91 +369,102 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			goff_of(gslot), s_ds + dslot * RADIX, start_bit, dmask, err_flag);
 	};
 
-	/* ---- prologue */
-	if (tid == 0) { s_misc[8] = atomicAdd(ticket, 1u); s_misc[10] = 0; s_misc[11] = 0; }
+	/* ---- prologue: two tickets (the next tile is always known one iteration ahead) */
+	if (tid == 0) { s_misc[8] = atomicAdd(ticket, 1u); s_misc[9] = atomicAdd(ticket, 1u); s_misc[10] = 0; s_misc[11] = 0; }
 	zero_row();
 	__syncthreads();
 	u32 cur = s_misc[8];
+	u32 nxt = s_misc[9];
 	if (cur >= num_tiles) return;
+	__syncthreads();
 	load_tile(cur);
 	{
-	/* ---- schedule with TWO iterations of slack between a tile's AGG and the use of its PREF:
-	 *   P1 count(k) | B1 | P2 digits(k) + PREF(k-2) -> offsets | B2 | write-out(k-2) | B3 |
-	 *   place(k) into the buffer just freed | load(k+1)
-	 * The prefix latency (propagator rounds, L2 round trips, slow neighbours) is then far from
-	 * the critical path and the propagators need no SM of their own.  The next tile's keys
-	 * are pulled into L2 as soon as its ticket is known, so the late load is an L2 hit. */
+	/* ---- schedule, TWO iterations of slack between a tile's AGG and the use of its PREF, two
+	 * CTA barriers per tile:
+	 *   P1 count(k) | B1 | warps 0-3: digits(k) -> AGG, bases  ||  the other warps: PREF(k-2) ->
+	 *   offsets, then write-out(k-2) | B2 | place(k) into the buffer just freed + load(k+1)
+	 * The latency-bound digit phase (128 threads) runs UNDER the write-out of the older tile
+	 * instead of in front of it.  The prefix latency (propagator rounds, L2 round trips, slow
+	 * neighbours) is far from the critical path and the propagators need no SM of their own.
+	 * Tickets are drawn two tiles ahead, so the next tile's keys are pulled into L2 a whole
+	 * iteration before they are loaded. */
 	u32 t1 = NONE, t2 = NONE;         /* tiles of the previous two iterations (staged, not yet written) */
 	int b = 0;                        /* buffer of the current tile (= buffer of t2) */
 	int s0 = 0, s1 = 2, s2 = 1;       /* s_ds slots of cur, t1, t2 (k, k-1, k-2 mod 3) */
-	const bool is_pref_thread = tid >= RADIX;
 	const LbT zero_w[DPT] = {};
+	constexpr int WO_T = THREADS - DT;        /* threads of the overlapped write-out */
 	for (;;) {
 		LbT wp[DPT] = {};
 		if (t2 != NONE && is_pref_thread) {
 #pragma unroll
-			for (int j = 0; j < DPT; ++j) wp[j] = ld_relaxed(pref + (size_t) t2 * RADIX + (tid - RADIX + j * PREF_T));
+			for (int j = 0; j < DPT; ++j) wp[j] = ld_relaxed(pref + (size_t) t2 * RADIX + (tid - DT + j * PREF_T));
 		}
 		const u32 cnt = tile_count_of(cur);
 		/* P1 count */
 		if (cnt == (u32) TILE) {
 #pragma unroll
-			for (int i = 0; i < IPT; ++i) atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+			for (int i = 0; i < IPT; ++i) row_count(v6_digit<ElemT>(key[i], start_bit, dmask));
 		} else {
 #pragma unroll
 			for (int i = 0; i < IPT; ++i)
-				if (wbase + i * 32u < cnt) atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+				if (wbase + i * 32u < cnt) row_count(v6_digit<ElemT>(key[i], start_bit, dmask));
 		}
 		mark(0);
 		__syncthreads();                                         /* B1 */
 		mark(1);
-		/* P2 */
-		if (tid < RADIX) {
+		bool bad = false;
+		if (tid < DT) {
+			/* P2: my two digits, 2 * tid (low halves) and 2 * tid + 1 (high halves) */
 			u32 c[WARPS];
 #pragma unroll
-			for (int w = 0; w < WARPS; ++w) c[w] = whist[w * RADIX + tid];
-			u32 count = 0;
+			for (int w = 0; w < WARPS; ++w) c[w] = whist[w * ROWW + tid];
+			u32 sum = 0;
 #pragma unroll
-			for (int w = 0; w < WARPS; ++w) count += c[w];
-			st_relaxed(agg + (size_t) cur * RADIX + tid, (LbT) (PPWord<LbT>::VALID | (LbT) count));
-			const u32 incl = warp_inclusive_scan<u32>(count, lane);
+			for (int w = 0; w < WARPS; ++w) sum += c[w];
+			const u32 c0 = sum & 0xffffu, c1 = sum >> 16;
+			st_relaxed(agg + (size_t) cur * RADIX + 2 * tid, (LbT) (PPWord<LbT>::VALID | (LbT) c0));
+			st_relaxed(agg + (size_t) cur * RADIX + 2 * tid + 1, (LbT) (PPWord<LbT>::VALID | (LbT) c1));
+			const u32 pair = c0 + c1;
+			const u32 incl = warp_inclusive_scan<u32>(pair, lane);
 			if (lane == 31) s_misc[warp] = incl;
-			named_bar_sync(1, RADIX);
+			named_bar_sync(1, DT);
 			u32 off = 0;
 #pragma unroll
-			for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[w];
-			u32 run = off + incl - count;
-			s_ds[s0 * RADIX + tid] = run;
+			for (int w = 0; w < DT / 32; ++w) if (w < warp) off += s_misc[w];
+			const u32 ds0 = off + incl - pair, ds1 = ds0 + c0;
+			*reinterpret_cast<uint2*>(s_ds + s0 * RADIX + 2 * tid) = make_uint2(ds0, ds1);
+			u32 run = ds0 | (ds1 << 16);
 #pragma unroll
-			for (int w = 0; w < WARPS; ++w) { whist[w * RADIX + tid] = run; run += c[w]; }
-		} else if (is_pref_thread) {
-			u32 nt = 0;
-			if (tid == RADIX) nt = atomicAdd(ticket, 1u);        /* in flight during the prefix wait */
-			if (t2 != NONE) prefix_to_goff(t2, 0, s2, wp);
-			if (tid == RADIX) s_misc[8] = nt;
+			for (int w = 0; w < WARPS; ++w) { whist[w * ROWW + tid] = run; run += c[w]; }
+			mark(2);
+		} else {
+			if (is_pref_thread) {
+				u32 nt = 0;
+				if (tid == DT) nt = atomicAdd(ticket, 1u);           /* the tile after next; in flight during the prefix wait */
+				if (t2 != NONE) prefix_to_goff(t2, 0, s2, wp);
+				if (tid == DT) s_misc[8] = nt;
+			}
+			/* P5 write-out of the tile staged two iterations ago (same buffer as the current tile) */
+			if (t2 != NONE) {
+				named_bar_sync(2, WO_T);
+				bad = write_out(t2, b, 0, true, DT, WO_T, 2);
+			}
 		}
-		mark(2);
-		__syncthreads();                                         /* B2 */
+		if (__syncthreads_or(bad ? 1 : 0)) repair(t2, b, 0, s2);   /* B2 */
 		mark(3);
-		const u32 nxt = s_misc[8];
+		const u32 nxt2 = s_misc[8];
 		const bool more = nxt < num_tiles;
-		if (more) {
-			/* next tile -> L2 (one 128-byte line per thread) */
-			const size_t lo = (size_t) nxt * TILE * sizeof(ElemT) + (size_t) tid * 128;
+		if (nxt2 < num_tiles) {
+			/* the tile after next -> L2 (one 128-byte line per thread) */
+			const size_t lo = (size_t) nxt2 * TILE * sizeof(ElemT) + (size_t) tid * 128;
 			if (lo < n * sizeof(ElemT) && (size_t) tid * 128 < (size_t) TILE * sizeof(ElemT))
 				asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(in) + lo));
 			if (HAS_VAL) {
-				const size_t lv = (size_t) nxt * TILE * 4 + (size_t) tid * 128;
+				const size_t lv = (size_t) nxt2 * TILE * 4 + (size_t) tid * 128;
 				if (lv < n * 4 && (size_t) tid * 128 < (size_t) TILE * 4)
 					asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(vin) + lv));
 			}
 		}
-		/* P5 write-out of the tile staged two iterations ago (same buffer as the current tile) */
-		bool bad = false;
-		if (t2 != NONE) bad = write_out(t2, b, 0, true);
-		mark(4);
-		if (__syncthreads_or(bad ? 1 : 0)) repair(t2, b, 0, s2);   /* B3 */
-		mark(5);
 		/* P3 place + P4 next tile: a key register is refilled as soon as its key is staged */
 		{
 			ElemT* skeys = buf_keys(b);
@@ -408,7 +476,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 				const u32* npv = vin + (size_t) nxt * TILE + wbase;
 #pragma unroll
 				for (int i = 0; i < IPT; ++i) {
-					const u32 p = atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+					const u32 p = row_take(v6_digit<ElemT>(key[i], start_bit, dmask));
 					skeys[p] = key[i];
 					key[i] = __ldcs(np + i * 32);
 					if (HAS_VAL) {
@@ -423,7 +491,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 #pragma unroll
 				for (int i = 0; i < IPT; ++i)
 					if (wbase + i * 32u < cnt) {
-						const u32 p = atomicAdd(&wh[v6_digit<ElemT>(key[i], start_bit, dmask)], 1u);
+						const u32 p = row_take(v6_digit<ElemT>(key[i], start_bit, dmask));
 						skeys[p] = key[i];
 						if (HAS_VAL) {
 							svals[p] = val[i];
@@ -441,6 +509,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		{ const int t = s2; s2 = s1; s1 = s0; s0 = t; }
 		if (!more) break;
 		cur = nxt;
+		nxt = nxt2;
 	}
 	/* ---- epilogue: t2 is staged in buffer b, t1 in buffer b^1 */
 	for (int r = 0; r < 2; ++r) {
@@ -451,15 +520,41 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		if (t == NONE) continue;
 		if (is_pref_thread) prefix_to_goff(t, 0, ss, zero_w);
 		__syncthreads();
-		const bool bad = write_out(t, bb, 0, true);
+		const bool bad = write_out(t, bb, 0, true, 0, THREADS, 0);
 		if (__syncthreads_or(bad ? 1 : 0)) repair(t, bb, 0, ss);
 	}
 	}
 }
 
+/* Are same-address shared-memory atomics of one warp instruction served in lane order?  The
+ * instruction form of the placement above (packed 16-bit counters, add with return) on
+ * addresses that collide from "sometimes" to "always"; out[0] counts violations against the
+ * __match_any_sync ranks, out[1] the samples. */
+__global__ void clo_radix_atomic_order_selftest_kernel(u32* __restrict__ out, u32 seed, int iters) {
+	__shared__ u32 row[16][RADIX / 2];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	u32 s = seed + threadIdx.x * 7919u + blockIdx.x * 104729u;
+	u32 bad = 0, tot = 0;
+	for (int it = 0; it < iters; ++it) {
+		reinterpret_cast<uint4*>(row[warp])[lane] = make_uint4(0u, 0u, 0u, 0u);
+		__syncwarp();
+		s = s * 1664525u + 1013904223u;
+		const u32 spread = (it & 3) == 0 ? 255u : ((it & 3) == 1 ? 15u : ((it & 3) == 2 ? 3u : 0u));
+		const u32 d = (s >> 24) & spread;
+		const u32 sh = (d & 1u) << 4;
+		const u32 old = (atomicAdd(&row[warp][d >> 1], 1u << sh) >> sh) & 0xffffu;
+		const u32 peers = __match_any_sync(0xffffffffu, d);
+		bad += (old != (u32) __popc(peers & ((1u << lane) - 1u)));
+		tot += 1;
+		__syncwarp();
+	}
+	atomicAdd(out, bad);
+	atomicAdd(out + 1, tot);
+}
+
 template <typename ElemT, int THREADS, int IPT, typename LbT, bool HAS_VAL = false>
 constexpr size_t onesweep_v6_smem() {
-	constexpr size_t worker = (size_t) (THREADS / 32) * RADIX * 4 + 4 * RADIX * 4 + 2 * RADIX * 8 + 16 * 4 +
+	constexpr size_t worker = (size_t) (THREADS / 32) * (RADIX / 2) * 4 + 4 * RADIX * 4 + 2 * RADIX * 8 + 16 * 4 +
 		2 * ((size_t) THREADS * IPT * sizeof(ElemT) + (HAS_VAL ? (size_t) THREADS * IPT * 6 : 0));
 	constexpr size_t prop = pp_propagate2_smem<LbT, THREADS, v6_prop_groups(THREADS, (int) sizeof(LbT))>();
 	return worker > prop ? worker : prop;

@@ -75,6 +75,8 @@ def main():
         names = ["zero+loadwait", "rank", "digit phase", "stage", "ticket+loadissue", "prefix wait", "write-out"]
         if os.environ.get("CLO_RADIX_KERNEL") is None:
             names = ["P1 count+loadwait", "B1 wait", "P2 digits", "B2 wait", "P5 write-out", "B3 wait", "P3 place+P4 load"]
+        if os.environ.get("CLO_RADIX_KERNEL") == "v7":
+            names = ["P1 count", "B1 wait", "P2 digits+PREF wait", "B2 wait", "P3 place+load", "B3 wait", "P4 write-out"]
         if os.environ.get("CLO_RADIX_KERNEL") == "classic":
             names = ["ticket+zero", "load", "rank", "digit phase", "stage", "look-back", "write-out"]
         tiles = 4 * ((n + 8191) // 8192)
@@ -85,7 +87,9 @@ def main():
                                        "walk_cycles": round(d[9] / tiles, 1), "walk_rounds": round(d[10] / tiles, 2),
                                        "walk_unpublished": round(d[11] / tiles, 2),
                                        "walk_depth": round(d[12] / tiles, 1),
-                                       "prop_cycles_total": d[14], "prop_rounds": d[15]}}), flush=True)
+                                       "prop_cycles_total": d[14], "prop_rounds": d[15],
+                                       "prop_idle_rounds": d[16], "prop_idle_cycles": d[17],
+                                       "prop_wait_bar_store_cycles": [d[11], d[12], d[13]]}}), flush=True)
         os.environ.pop("CLO_RADIX_PROFILE")
         b_in.destroy(); b_out.destroy(); s.destroy(); del t_in, t_out
         torch.cuda.empty_cache()
