@@ -12,8 +12,12 @@ KNUTH(x) hash, main_seed 0 (bit-exact against the oracle, so the input is reprod
                                                                 the host cores (oracle port)
 
 N > 1 (under torchrun): every rank holds 2^28 keys (weak scaling); the ranks sort the
-N * 2^28 keys as one sequence with the sample sort of cl_ops_b200/dist.py (NCCL
-all-to-all-v exchange); value = all keys / max-over-ranks time.
+N * 2^28 keys as one sequence with the sample sort of cl_ops_b200/dist.py (fused partition +
+peer-memory scatter over NVLink; NCCL carries only samples, bucket sizes and the barrier);
+value = all keys / max-over-ranks time.  "secondary" in the JSON line holds the other
+BASELINE.json configs measured by the same run: scans of 2^30 elements, 2^32 RNG words, the
+2^20 sbitonic sort, the 2^30 key-value sort (uniform and Zipf) and the headline sort on
+skewed keys -- each with its parity check.
 
 Prints ONE JSON line (rank 0).  Timing: CUDA events on the launching stream, barrier +
 synchronize on both sides, max over ranks; inputs (1 GiB per rank) are larger than the
@@ -119,6 +123,285 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# --------------------------------------------------------------------------------------
+# secondary lines: the other BASELINE.json configs, measured by the same run
+# --------------------------------------------------------------------------------------
+
+def _dev_ms(torch, fn, iters=5, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def _xor_reduce(torch, x):
+    """xor of all elements of an int64 tensor (torch has no xor reduction: halve until one is left)."""
+    acc = 0
+    while x.numel() > 1:
+        if x.numel() % 2:
+            acc ^= int(x[-1].item())
+            x = x[:-1]
+        h = x.numel() // 2
+        x = torch.bitwise_xor(x[:h], x[h:])
+    return acc ^ (int(x[0].item()) if x.numel() else 0)
+
+
+def _zipf_u32(torch, n, seed):
+    """Zipf(s = 1) over 2^20 distinct values, ranks hashed with Knuth's multiplier."""
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    u = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
+    rank = torch.exp(u * float(np.log(1 << 20))).to(torch.int64).clamp_(1, 1 << 20)
+    return ((rank * 2654435761) & 0xFFFFFFFF).to(torch.int32)
+
+
+def _zipf_u64(torch, n, seed):
+    """Zipf(s = 1) over 2^24 distinct values, key = rank * 0x9E3779B97F4A7C15 mod 2^64."""
+    g = torch.Generator(device="cuda"); g.manual_seed(seed)
+    u = torch.rand(n, device="cuda", generator=g, dtype=torch.float64)
+    rank = torch.exp(u * float(np.log(1 << 24))).to(torch.int64).clamp_(1, 1 << 24)
+    return rank * -7046029254386353131
+
+
+def secondary_single(torch, clo, ctx, queue, peak, sorter, log2n):
+    """configs C1, C2 (skewed), C3, C4, C5 on one GPU: device time (CUDA events), inputs in HBM."""
+    W = clo.Buffer.wrap_tensor
+    sec = {}
+    n = 1 << log2n
+    # -- C2 on skewed keys: Zipf(1.0) and already sorted input, the headline sorter
+    out = torch.empty(n, dtype=torch.int32, device="cuda")
+    bo = W(ctx, out)
+    for name, keys in (("sort_u32_zipf", _zipf_u32(torch, n, 1)), ("sort_u32_sorted", torch.arange(n, dtype=torch.int32, device="cuda"))):
+        bi = W(ctx, keys)
+        ms = _dev_ms(torch, lambda: sorter.with_device_data(queue, bi, bo, n))
+        u = out.to(torch.int64) & 0xFFFFFFFF
+        ok = bool((u[1:] >= u[:-1]).all().item()) and int(u.sum().item()) == int((keys.to(torch.int64) & 0xFFFFFFFF).sum().item())
+        sec[name] = {"n": n, "ms": ms, "gkeys_s": n / ms / 1e6, "frac": BYTES_PER_KEY * n / ms / 1e6 / peak, "sorted_permutation": ok}
+        bi.destroy(); del keys, u
+    bo.destroy(); del out
+    torch.cuda.empty_cache()
+    # -- C1: sbitonic, 2^20 u32 (the reference's CPU-runnable case)
+    nb = 1 << 20
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    a0 = torch.randint(-2**31, 2**31 - 1, (nb,), dtype=torch.int32, device="cuda", generator=g)
+    t = torch.empty_like(a0)
+    bt = W(ctx, t)
+    sb = clo.CloSort("sbitonic", ctx, clo.UINT)
+
+    def run_bitonic():
+        t.copy_(a0)
+        sb.with_device_data(queue, bt, None, nb)
+    ms_all = _dev_ms(torch, run_bitonic, iters=20)
+    ms_copy = _dev_ms(torch, lambda: t.copy_(a0), iters=20)
+    run_bitonic()
+    u = t.to(torch.int64) & 0xFFFFFFFF
+    ok = bool((u[1:] >= u[:-1]).all().item()) and int(u.sum().item()) == int((a0.to(torch.int64) & 0xFFFFFFFF).sum().item())
+    sec["sbitonic_u32_2p20"] = {"n": nb, "ms": ms_all - ms_copy, "mkeys_s": nb / (ms_all - ms_copy) / 1e3, "sorted_permutation": ok,
+                                "note": "in place; the restoring copy of the input is timed separately and subtracted"}
+    bt.destroy(); sb.destroy(); del a0, t, u
+    # -- C4: exclusive scans of 2^30 elements
+    ns = 1 << 30
+    g = torch.Generator(device="cuda"); g.manual_seed(4)
+    x = torch.randint(0, 128, (ns,), dtype=torch.int32, device="cuda", generator=g)
+    for name, st, sdt, bpe in (("scan_u32_u32", clo.UINT, torch.int32, 8), ("scan_u32_u64", clo.ULONG, torch.int64, 12)):
+        o = torch.empty(ns, dtype=sdt, device="cuda")
+        sc = clo.CloScan("blelloch", ctx, clo.UINT, st)
+        bi, bo = W(ctx, x), W(ctx, o)
+        ms = _dev_ms(torch, lambda: sc.with_device_data(queue, bi, bo, ns))
+        ref = torch.cumsum(x.to(torch.int64), 0) - x
+        m = 0xFFFFFFFF if sdt == torch.int32 else -1
+        ok = bool(torch.equal(o.to(torch.int64) & m, ref & m))
+        sec[name] = {"n": ns, "ms": ms, "gbs": bpe * ns / ms / 1e6, "frac": bpe * ns / ms / 1e6 / peak, "bytes_per_elem": bpe, "bit_exact": ok}
+        bi.destroy(); bo.destroy(); sc.destroy(); del o, ref
+    del x
+    torch.cuda.empty_cache()
+    xf = torch.rand(ns, dtype=torch.float32, device="cuda", generator=g)
+    o = torch.empty(ns, dtype=torch.float32, device="cuda")
+    sc = clo.CloScan("blelloch", ctx, clo.FLOAT, clo.FLOAT)
+    bi, bo = W(ctx, xf), W(ctx, o)
+    ms = _dev_ms(torch, lambda: sc.with_device_data(queue, bi, bo, ns))
+    ref = torch.cumsum(xf.to(torch.float64), 0) - xf.to(torch.float64)
+    err = (o.to(torch.float64) - ref).abs()
+    sec["scan_f32"] = {"n": ns, "ms": ms, "gbs": 8.0 * ns / ms / 1e6, "frac": 8.0 * ns / ms / 1e6 / peak, "bytes_per_elem": 8,
+                       "tolerance": "|gpu - ref| <= 1e-5 * |ref| + 1e-3 against an f64 prefix sum",
+                       "within_tolerance": bool((err <= 1e-5 * ref.abs() + 1e-3).all().item()),
+                       "max_rel_err": float((err / ref.abs().clamp_min(1.0)).max().item())}
+    bi.destroy(); bo.destroy(); sc.destroy(); del xf, o, ref, err
+    torch.cuda.empty_cache()
+    # -- C5: 2^32 words of xorshift128 / mwc64x (2^22 streams x 2^10 runs), slice checked against the oracle
+    import oracle
+    G, runs = 1 << 22, 1 << 10
+    o = torch.empty(G * runs, dtype=torch.int32, device="cuda")
+    bo = W(ctx, o)
+    for name in ("xorshift128", "mwc64x"):
+        r = clo.CloRng(name, ctx, clo.SEED_DEV_GID, None, G, 0, "KNUTH(x)", queue)
+        r.generate(queue, bo, runs); torch.cuda.synchronize(); r.destroy()
+        r = clo.CloRng(name, ctx, clo.SEED_DEV_GID, None, G, 0, "KNUTH(x)", queue)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); r.generate(queue, bo, runs); b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b); r.destroy()
+        SG, SR = 1 << 16, 16
+        seeds = oracle.rng_seeds_dev_gid(name, 1, 0, SG)
+        want, _ = oracle.rng_generate(name, seeds, SG, SR)
+        got = o.view(runs, G)[:SR, :SG].contiguous().cpu().numpy().view(np.uint32).reshape(-1)
+        sec["rng_" + name] = {"words": G * runs, "ms": ms, "gwords_s": G * runs / ms / 1e6, "gbs": 4.0 * G * runs / ms / 1e6,
+                              "frac": 4.0 * G * runs / ms / 1e6 / peak, "slice": "streams [0, 2^16) x runs [0, 16)",
+                              "slice_bit_exact_vs_oracle": bool(np.array_equal(got, np.asarray(want).reshape(-1)))}
+    bo.destroy(); del o
+    torch.cuda.empty_cache()
+    # -- C3: key-value sort of 2^30 (u64 key, u32 payload = index), uniform and Zipf
+    nk = 1 << 30
+    s64 = clo.CloSort("satradix", ctx, clo.ULONG)
+    for name in ("kv_u64_u32_uniform", "kv_u64_u32_zipf"):
+        g = torch.Generator(device="cuda"); g.manual_seed(3)
+        keys0 = torch.randint(-2**63, 2**63 - 1, (nk,), dtype=torch.int64, device="cuda", generator=g) if name.endswith("uniform") else _zipf_u64(torch, nk, 3)
+        keys = keys0.clone(); pay = torch.arange(nk, dtype=torch.int32, device="cuda")
+        bk, bp = W(ctx, keys), W(ctx, pay)
+        s64.pairs_with_device_data(queue, bk, bp, nk); torch.cuda.synchronize()
+        keys.copy_(keys0); pay.copy_(torch.arange(nk, dtype=torch.int32, device="cuda")); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); s64.pairs_with_device_data(queue, bk, bp, nk); b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        uk = keys ^ (-2**63)
+        srt = bool((uk[1:] >= uk[:-1]).all().item())
+        eq = uk[1:] == uk[:-1]
+        stable = bool((pay[1:][eq] > pay[:-1][eq]).all().item())
+        del uk, eq
+        src_ok = bool(torch.equal(keys0[pay.to(torch.int64)], keys))
+        sec[name] = {"n": nk, "ms": ms, "gpairs_s": nk / ms / 1e6, "gbs": 200.0 * nk / ms / 1e6, "frac": 200.0 * nk / ms / 1e6 / peak,
+                     "bytes_per_pair": 200, "sorted": srt, "stable": stable, "payload_is_source_index": src_ok}
+        bk.destroy(); bp.destroy(); del keys, pay, keys0
+        torch.cuda.empty_cache()
+    s64.destroy()
+    return sec
+
+
+def secondary_multi(torch, dist, clo, cdist, ctx, queue, peak, rank, world):
+    """configs C3, C4, C5 across the GPUs of the job: device time, max over ranks."""
+    W = clo.Buffer.wrap_tensor
+    sec = {}
+
+    def maxms(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); return float(t.item())
+
+    def all_ok(ok):
+        t = torch.tensor([1 if ok else 0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN); return bool(t.item())
+    # -- C4: 2^30 elements per GPU: reduce -> all-gather of totals -> scan with a device-resident carry
+    n = 1 << 30
+    for name, et, st, edt in (("scan_u32_u32", clo.UINT, clo.UINT, torch.int32), ("scan_f32", clo.FLOAT, clo.FLOAT, torch.float32)):
+        g = torch.Generator(device="cuda"); g.manual_seed(7 + rank)
+        x = torch.randint(0, 128, (n,), dtype=torch.int32, device="cuda", generator=g) if edt == torch.int32 else torch.rand(n, dtype=torch.float32, device="cuda", generator=g)
+        out = torch.empty(n, dtype=edt, device="cuda")
+        sc = clo.CloScan("blelloch", ctx, et, st)
+        tot = torch.zeros(1, dtype=edt, device="cuda")
+
+        def red(d):
+            b1, b2 = W(ctx, d), W(ctx, tot)
+            sc.reduce_with_device_data(queue, b1, b2, d.numel()); b1.destroy(); b2.destroy()
+            return tot
+
+        def scan(d, carry):
+            b1, b2, b3 = W(ctx, d), W(ctx, out), W(ctx, carry)
+            sc.with_device_data(queue, b1, b2, d.numel(), carry_in=b3); b1.destroy(); b2.destroy(); b3.destroy()
+            return out
+        for _ in range(2):
+            cdist.dist_scan(red, scan, x, edt)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(5):
+            cdist.dist_scan(red, scan, x, edt)
+        b.record(); torch.cuda.synchronize()
+        ms = maxms(a.elapsed_time(b) / 5)
+        wide = torch.int64 if edt == torch.int32 else torch.float64
+        mytot = x.to(wide).sum().reshape(1)
+        alltot = torch.empty(world, dtype=wide, device="cuda"); dist.all_gather_into_tensor(alltot, mytot)
+        carry = alltot[:rank].sum()
+        ref = torch.cumsum(x.to(wide), 0) - x.to(wide) + carry
+        if edt == torch.int32:
+            ok = all_ok(bool(torch.equal(out.to(torch.int64) & 0xFFFFFFFF, ref & 0xFFFFFFFF)))
+            extra = {"bit_exact": ok}
+        else:
+            err = (out.to(torch.float64) - ref).abs()
+            ok = all_ok(bool((err <= 1e-5 * ref.abs() + 1e-3).all().item()))
+            extra = {"within_tolerance": ok, "tolerance": "|gpu - ref| <= 1e-5 * |ref| + 1e-3 against an f64 prefix sum"}
+            del err
+        sec[name] = {"n_per_gpu": n, "ms": ms, "aggregate_gbs": world * 12.0 * n / ms / 1e6, "bytes_per_elem": 12,
+                     "frac_per_gpu": 12.0 * n / ms / 1e6 / peak}
+        sec[name].update(extra)
+        sc.destroy(); del x, out, ref
+        torch.cuda.empty_cache()
+    # -- C5: 2^32 words over the GPUs, streams partitioned by a gid offset (no communication)
+    import oracle
+    G_total, runs = 1 << 22, 1 << 10
+    first, count = cdist.rng_partition(G_total)
+    o = torch.empty(count * runs, dtype=torch.int32, device="cuda")
+    bo = W(ctx, o)
+    for name in ("xorshift128", "mwc64x"):
+        rg = clo.CloRng(name, ctx, seeds_count=count, main_seed=0, hash="KNUTH(x)", queue=queue, gid_offset=first)
+        rg.generate(queue, bo, runs); torch.cuda.synchronize(); rg.destroy()
+        rg = clo.CloRng(name, ctx, seeds_count=count, main_seed=0, hash="KNUTH(x)", queue=queue, gid_offset=first)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); rg.generate(queue, bo, runs); b.record(); torch.cuda.synchronize()
+        ms = maxms(a.elapsed_time(b)); rg.destroy()
+        SG, SR = 4096, 8
+        ok = True
+        for g0 in (0, count - SG):
+            seeds = oracle.rng_seeds_dev_gid(name, 1, 0, SG, gid0=first + g0)
+            want, _ = oracle.rng_generate(name, seeds, SG, SR)
+            got = o.view(runs, count)[:SR, g0:g0 + SG].contiguous().cpu().numpy().view(np.uint32)
+            ok &= bool(np.array_equal(got, want))
+        sec["rng_" + name] = {"words": G_total * runs, "ms": ms, "aggregate_gwords_s": G_total * runs / ms / 1e6,
+                              "aggregate_gbs": 4.0 * G_total * runs / ms / 1e6, "slices_bit_exact_vs_oracle": all_ok(ok)}
+    bo.destroy(); del o
+    torch.cuda.empty_cache()
+    # -- C3: key-value sample sort of 2^30 pairs in total (u64 key, u32 payload = global index)
+    n = (1 << 30) // world
+    ops = cdist.GpuOps(clo, ctx, queue, clo.ULONG)
+    ops.setup_peer_exchange(n + n // 2, torch.int64, True)
+    for name in ("kv_u64_u32_uniform", "kv_u64_u32_zipf"):
+        g = torch.Generator(device="cuda"); g.manual_seed(100 + rank)
+        keys = torch.randint(-2**63, 2**63 - 1, (n,), dtype=torch.int64, device="cuda", generator=g) if name.endswith("uniform") else _zipf_u64(torch, n, 100 + rank)
+        pay = (torch.arange(n, dtype=torch.int64, device="cuda") + rank * n).to(torch.int32)
+        for _ in range(2):
+            cdist.sample_sort(keys, pay, ops, 64, gidx0=rank * n)
+        torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            k, pp, info = cdist.sample_sort(keys, pay, ops, 64, gidx0=rank * n)
+        b.record(); torch.cuda.synchronize()
+        ms = maxms(a.elapsed_time(b) / 3)
+        uk = k ^ (-2**63)
+        ok = bool((uk[1:] >= uk[:-1]).all().item()) if uk.numel() > 1 else True
+        eq = uk[1:] == uk[:-1]
+        pl = pp.to(torch.int64) & 0xFFFFFFFF
+        stable = bool((pl[1:][eq] > pl[:-1][eq]).all().item())      # payload = global index (2^30 pairs fit 32 bits)
+        edges = torch.zeros(2 * world, dtype=torch.int64, device="cuda")
+        if uk.numel():
+            edges[2 * rank], edges[2 * rank + 1] = uk[0], uk[-1]
+        dist.all_reduce(edges)
+        # permutation: count, sum and xor of keys and of payloads over all ranks, before and after
+        chk = torch.stack([torch.tensor(k.numel(), device="cuda"), k.sum(), pl.sum(), -torch.tensor(n, device="cuda"), -keys.sum(), -(pay.to(torch.int64) & 0xFFFFFFFF).sum()]).to(torch.int64)
+        dist.all_reduce(chk)
+        e = edges.tolist()
+        c = chk.tolist()
+        ok = ok and all(e[2 * i + 1] <= e[2 * i + 2] for i in range(world - 1)) and c[0] + c[3] == 0 and c[1] + c[4] == 0 and c[2] + c[5] == 0
+        sec[name] = {"pairs_total": world * n, "ms": ms, "gpairs_s": world * n / ms / 1e6, "sorted_permutation": all_ok(ok),
+                     "globally_stable": all_ok(stable), "fused_peer_scatter": bool(info.get("fused")), "received_rank0": info["received"]}
+        del keys, pay, k, pp, uk, eq, pl
+        torch.cuda.empty_cache()
+    ops.close()
+    return sec
 
 
 # --------------------------------------------------------------------------------------
@@ -230,21 +513,62 @@ def run_ours(args):
         if u.numel():
             edges[2 * rank], edges[2 * rank + 1] = u[0], u[-1]
         dist.all_reduce(edges)
-        cnt = torch.tensor([u.numel()], dtype=torch.int64, device="cuda")
+        # a permutation of the input: count, sum and xor of all keys, before and after
+        uin = t_in.to(torch.int64) & 0xFFFFFFFF
+        xin, xout = _xor_reduce(torch, uin), _xor_reduce(torch, u)
+        cnt = torch.stack([torch.tensor(u.numel(), device="cuda") - n, u.sum() - uin.sum()]).to(torch.int64)
         dist.all_reduce(cnt)
+        xr = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+        mine = torch.tensor([xin, xout], dtype=torch.int64, device="cuda")
+        dist.all_gather(xr, mine)
+        x_in = x_out = 0
+        for v in xr:
+            a_, b_ = v.tolist()
+            x_in ^= a_; x_out ^= b_
+        del uin
         e = edges.tolist()
-        ok = ok and all(e[2 * i + 1] <= e[2 * i + 2] for i in range(world - 1)) and int(cnt.item()) == world * n
+        ok = ok and all(e[2 * i + 1] <= e[2 * i + 2] for i in range(world - 1)) and cnt.tolist() == [0, 0] and x_in == x_out
         okt = torch.tensor([1 if ok else 0], device="cuda")
         dist.all_reduce(okt, op=dist.ReduceOp.MIN)
         ok = bool(okt.item())
         dbg = ops.sorter.debug(queue)
         del u, k_sorted
 
+    # ---- the other BASELINE.json configs, same run (device time)
+    secondary = None
+    if not args.no_secondary:
+        if distributed:
+            secondary = secondary_multi(torch, dist, clo, cdist, ctx, queue, peak, rank, world)
+        else:
+            del t_out
+            b_out.destroy()
+            torch.cuda.empty_cache()
+            secondary = secondary_single(torch, clo, ctx, queue, peak, sorter, args.log2n)
+            t_out = torch.empty_like(t_in)
+            b_out = clo.Buffer.wrap_tensor(ctx, t_out)
+
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timing
     e2e = None
-    e2e_steps = max(1, min(3, args.steps))
+    e2e_steps = max(10, min(20, args.steps))
     h_in = torch.empty(n, dtype=torch.int32).pin_memory()
     h_in.copy_(t_in.cpu())
+    # the floor of any host-buffer path on this box: the same bytes in and out as plain pinned
+    # copies, one cudaMemcpyAsync each way, nothing else
+    h_floor = torch.empty(n, dtype=torch.int32).pin_memory()
+    d_floor = torch.empty(n, dtype=torch.int32, device="cuda")
+    for _ in range(2):
+        d_floor.copy_(h_in, non_blocking=True); h_floor.copy_(d_floor, non_blocking=True); torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        d_floor.copy_(h_in, non_blocking=True); h_floor.copy_(d_floor, non_blocking=True); torch.cuda.synchronize()
+    floor_dt = (time.perf_counter() - t0) / 5
+    if distributed:
+        tf = torch.tensor([floor_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tf, op=dist.ReduceOp.MAX)
+        floor_dt = float(tf.item())
+    del h_floor, d_floor
     if not distributed:
         h_out = torch.empty(n, dtype=torch.int32).pin_memory()
         e2e_sorter = clo.CloSort("satradix", ctx, clo.UINT)
@@ -261,7 +585,8 @@ def run_ours(args):
         assert bool(np.all(ho[1:] >= ho[:-1]))
         e2e = {"value": n / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n,
                "ms_per_step": dt * 1e3, "steps": e2e_steps, "n_gpus": 1,
-               "api": "clo_sort_with_host_data (pinned host buffers, device alloc + H2D + sort + D2H per call)"}
+               "pcie_floor_ms": floor_dt * 1e3, "frac_of_pcie_floor": floor_dt / dt,
+               "api": "clo_sort_with_host_data (pinned host buffers: H2D + sort + D2H per call)"}
         e2e_sorter.destroy()
         del h_out
     else:
@@ -290,6 +615,7 @@ def run_ours(args):
         assert bool(np.all(ho[1:] >= ho[:-1]))
         e2e = {"value": world * n / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": 4 * n * world,
                "d2h_bytes_per_step": 4 * n * world, "ms_per_step": dt * 1e3, "steps": e2e_steps, "n_gpus": world,
+               "pcie_floor_ms": floor_dt * 1e3, "frac_of_pcie_floor": floor_dt / dt,
                "api": "per rank: pinned host shard -> device, cl_ops_b200.dist.sample_sort, sorted slice -> pinned host; max over ranks"}
         del h_out, d_in
     del h_in
@@ -326,13 +652,13 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "satradix-equivalent LSD radix sort of 2^%d uint32 keys per GPU" % args.log2n
-                       + (" (sample sort across %d GPUs, NCCL all-to-all-v)" % world if distributed else ""),
+                       + (" (sample sort across %d GPUs: fused partition + CUDA-IPC peer-memory scatter over NVLink; NCCL carries samples, sizes and the barrier)" % world if distributed else ""),
                        "keys_per_gpu": n, "keys": "xorshift128 DEV_GID KNUTH(x) main_seed 0",
                        "api": "clo_sort_new('satradix') + clo_sort_with_device_data (out of place)",
                        "l2": "inputs (1 GiB/GPU) larger than L2, no flush", "parallelism": "sample-sort x%d" % world},
             "clocks": clocks, "gpu_launches": int(launches), "verified_sorted": ok,
             "repaired_tiles": int(dbg[1]), "lookback_timeout": int(dbg[0]),
-            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "secondary": secondary,
         }
         if distributed:
             out["phases_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
@@ -363,6 +689,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2n", type=int, default=LOG2N)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary lines (other BASELINE configs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -38,6 +38,9 @@
  *     CLO_RADIX_VERIFY=1 forces the verified instance; flag 16 plants a real inversion in
  *     front of the detector (tests).
  */
+#ifndef CLO_NO_SWIZZLE
+#define CLO_NO_SWIZZLE 0
+#endif
 #ifndef CLO_RADIX_V6_CUH
 #define CLO_RADIX_V6_CUH
 
@@ -198,11 +201,11 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	u32* whist = reinterpret_cast<u32*>(smem_raw);                          /* [WARPS][ROWW] packed: digit d = half (d & 1) of word d >> 1 */
 	u32* s_ds = whist + WARPS * ROWW;                                       /* [3][RADIX] digit starts (+1 pad) */
 	u64* s_goff_raw = reinterpret_cast<u64*>(s_ds + 4 * RADIX);             /* [2][RADIX] u64-sized slots (s_ds has 3 live slots + 1 pad) */
-	u32* s_misc = reinterpret_cast<u32*>(s_goff_raw + 2 * RADIX);           /* [16]: 0..7 scan, 8 ticket, 10..11 bad */
+	u32* s_misc = reinterpret_cast<u32*>(s_goff_raw + 2 * RADIX);           /* [32]: 0..7 scan, 8..9 tickets, 12..15 warp maxima, 16 heaviest digit */
 	/* staging, per buffer: keys [TILE]; with a payload also values [TILE] and the index in tile
 	 * of every staged element [TILE] (u16), which is what the stability check compares */
 	constexpr size_t BUF_BYTES = (size_t) TILE * sizeof(ElemT) + (HAS_VAL ? (size_t) TILE * 6 : 0);
-	unsigned char* s_buf_raw = reinterpret_cast<unsigned char*>(s_misc + 16);   /* [2][BUF_BYTES] */
+	unsigned char* s_buf_raw = reinterpret_cast<unsigned char*>(s_misc + 32);   /* [2][BUF_BYTES] */
 	auto buf_keys = [&](int b) { return reinterpret_cast<ElemT*>(s_buf_raw + (size_t) b * BUF_BYTES); };
 	auto buf_vals = [&](int b) { return reinterpret_cast<u32*>(s_buf_raw + (size_t) b * BUF_BYTES + (size_t) TILE * sizeof(ElemT)); };
 	auto buf_info = [&](int b) { return reinterpret_cast<unsigned short*>(s_buf_raw + (size_t) b * BUF_BYTES + (size_t) TILE * (sizeof(ElemT) + 4)); };
@@ -264,6 +267,32 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		const u32 sh = (d & 1u) << 4;
 		return (atomicAdd(&wh[d >> 1], 1u << sh) >> sh) & 0xffffu;
 	};
+	/* Skewed or clustered digits: lanes of one warp instruction that hit one address serialise in
+	 * the atomic unit (tools/ubench_atoms_dup.cu: one cycle per lane, 32 for a constant digit,
+	 * with or without a return value once the addend is not the constant 1).  A warp then counts
+	 * and places the keys of two CANDIDATE digits with ballots instead (deterministic, stable, no
+	 * atomic): the digit of its first key, and either the heaviest digit of the last counted tile
+	 * (when that digit holds >= 1/8 of the tile) or the digit of its last key (sorted or clustered
+	 * input -- also what every pass after the first sees when keys repeat -- where the 512 keys
+	 * of a warp span at most two digits).  A warp takes the path when the tile before was heavy
+	 * or when its first 32 keys mostly agree -- and looks at all only when the last counted tile was
+	 * LUMPY (some digit with >= 1/64 of the keys, four times the mean; uniform keys never are), so
+	 * ordinary tiles keep the plain atomics at the cost of one register compare. */
+	auto skew_mode = [&](bool heavy, bool lumpy) -> bool {
+		if (!lumpy || (flags & 32)) return false;      /* flag 32: A/B switch, plain atomics whatever the digits are */
+		const u32 d0 = v6_digit<ElemT>(key[0], start_bit, dmask);
+		return heavy || __popc(__ballot_sync(0xffffffffu, d0 == __shfl_sync(0xffffffffu, d0, 0))) >= 16;
+	};
+	auto skew_candidates = [&](bool heavy, u32 heavy_digit, u32& h1, u32& h2) {
+		h2 = __shfl_sync(0xffffffffu, v6_digit<ElemT>(key[0], start_bit, dmask), 0);
+		h1 = heavy ? heavy_digit : __shfl_sync(0xffffffffu, v6_digit<ElemT>(key[IPT - 1], start_bit, dmask), 31);
+		if (h1 == h2) h1 = 0x100u;
+	};
+	/* staging slot -> position: an XOR swizzle of the low five bits, so that the 32 lanes of a
+	 * placement hit 32 banks also when their slots are a multiple of 32 apart (sorted input: lane
+	 * l places digit d0 + l, and every digit run of the tile is 32 keys long); a linear, 32-aligned
+	 * read of the write-out stays conflict free */
+	auto sw = [](u32 j) -> u32 { return CLO_NO_SWIZZLE ? j : (j ^ ((j >> 5) & 31u)); };
 	/* coalesced write-out of a staged tile; returns true when the staged order is not
 	 * sorted on the bits processed so far (= some warp instruction's atomics were not
 	 * applied in lane order) */
@@ -285,13 +314,14 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 				u32* wv = const_cast<u32*>(svals);
 				unsigned short* wi = const_cast<unsigned short*>(sinfo);
 				for (u32 j = 1; j < cnt; ++j) {
-					const ElemT a = wk[j - 1], b2 = wk[j];
+					const u32 ja = sw(j - 1), jb = sw(j);
+					const ElemT a = wk[ja], b2 = wk[jb];
 					if (v6_digit<ElemT>(a, start_bit, dmask) != v6_digit<ElemT>(b2, start_bit, dmask)) continue;
 					if (!HAS_VAL && (a & low_mask) == (b2 & low_mask)) continue;
-					wk[j - 1] = b2; wk[j] = a;
+					wk[ja] = b2; wk[jb] = a;
 					if (HAS_VAL) {
-						const u32 v = wv[j - 1]; wv[j - 1] = wv[j]; wv[j] = v;
-						const unsigned short x = wi[j - 1]; wi[j - 1] = wi[j]; wi[j] = x;
+						const u32 v = wv[ja]; wv[ja] = wv[jb]; wv[jb] = v;
+						const unsigned short x = wi[ja]; wi[ja] = wi[jb]; wi[jb] = x;
 					}
 					atomicAdd(err_flag + 2, 1);
 					break;
@@ -303,28 +333,30 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			/* test hook: write this tile WRONG and report it, so that only a working repair
 			 * path gives a sorted result */
 			for (u32 j = lid; j < cnt; j += (u32) nthr) {
-				const ElemT k = skeys[j];
+				const ElemT k = skeys[sw(j)];
 				const LbT o = goff[v6_digit<ElemT>(k, start_bit, dmask)] + (LbT) j;
 				out[o] = (ElemT) ~k;
-				if (HAS_VAL) vout[o] = ~svals[j];
+				if (HAS_VAL) vout[o] = ~svals[sw(j)];
 			}
 			return true;
 		}
 		auto one = [&](u32 j) {
-			const ElemT k = skeys[j];
+			const u32 js = sw(j);
+			const ElemT k = skeys[js];
 			const u32 d = v6_digit<ElemT>(k, start_bit, dmask);
 			if (VERIFY) {
-				const ElemT kp = skeys[j > 0 ? j - 1 : 0];
+				const u32 jp = sw(j > 0 ? j - 1 : 0);
+				const ElemT kp = skeys[jp];
 				if (HAS_VAL) {
 					/* equal digits must keep their order in the tile (payloads tell equal keys apart) */
-					if (j > 0 && v6_digit<ElemT>(kp, start_bit, dmask) == d && sinfo[j] <= sinfo[j - 1]) bad = true;
+					if (j > 0 && v6_digit<ElemT>(kp, start_bit, dmask) == d && sinfo[js] <= sinfo[jp]) bad = true;
 				} else {
 					if ((k & low_mask) < (kp & low_mask)) bad = true;
 				}
 			}
 			const LbT o = goff[d] + (LbT) j;
 			out[o] = k;
-			if (HAS_VAL) vout[o] = svals[j];
+			if (HAS_VAL) vout[o] = svals[js];
 		};
 		if (nthr == THREADS) {
 			if (cnt == (u32) TILE) {
@@ -338,11 +370,15 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 				}
 			}
 		} else {
-			constexpr int ROUNDS = (TILE + (THREADS - DT) - 1) / (THREADS - DT);
+			/* the write-out that runs beside the digit phase: THREADS - DT threads */
+			constexpr int WT = THREADS - DT, FULL = TILE / WT, REM = TILE - FULL * WT;
+			if (cnt == (u32) TILE) {
 #pragma unroll
-			for (int i = 0; i < ROUNDS; ++i) {
-				const u32 j = lid + i * (u32) (THREADS - DT);
-				if (j < cnt) one(j);
+				for (int i = 0; i < FULL; ++i) one(lid + i * (u32) WT);
+				if (REM > 0 && lid < (u32) REM) one(lid + FULL * (u32) WT);
+			} else {
+#pragma unroll 1
+				for (u32 j = lid; j < cnt; j += (u32) WT) one(j);
 			}
 		}
 		return verify && bad;
@@ -393,6 +429,9 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	int s0 = 0, s1 = 2, s2 = 1;       /* s_ds slots of cur, t1, t2 (k, k-1, k-2 mod 3) */
 	const LbT zero_w[DPT] = {};
 	constexpr int WO_T = THREADS - DT;        /* threads of the overlapped write-out */
+	bool lumpy = false;                       /* the last counted tile has a digit with >= 1/64 of its keys */
+	bool heavy = false;                       /* ... with >= 1/8 of its keys ... */
+	u32 heavy_digit = 0;                      /* ... this one */
 	for (;;) {
 		LbT wp[DPT] = {};
 		if (t2 != NONE && is_pref_thread) {
@@ -401,7 +440,21 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		}
 		const u32 cnt = tile_count_of(cur);
 		/* P1 count */
-		if (cnt == (u32) TILE) {
+		if (cnt == (u32) TILE && skew_mode(heavy, lumpy)) {
+			u32 h1, h2, c1 = 0, c2 = 0;
+			skew_candidates(heavy, heavy_digit, h1, h2);
+#pragma unroll
+			for (int i = 0; i < IPT; ++i) {
+				const u32 d = v6_digit<ElemT>(key[i], start_bit, dmask);
+				c1 += __popc(__ballot_sync(0xffffffffu, d == h1));
+				c2 += __popc(__ballot_sync(0xffffffffu, d == h2));
+				if (d != h1 && d != h2) row_count(d);
+			}
+			if (lane == 0) {
+				if (c1) atomicAdd(&wh[h1 >> 1], c1 << ((h1 & 1u) << 4));
+				if (c2) atomicAdd(&wh[h2 >> 1], c2 << ((h2 & 1u) << 4));
+			}
+		} else if (cnt == (u32) TILE) {
 #pragma unroll
 			for (int i = 0; i < IPT; ++i) row_count(v6_digit<ElemT>(key[i], start_bit, dmask));
 		} else {
@@ -422,6 +475,14 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 #pragma unroll
 			for (int w = 0; w < WARPS; ++w) sum += c[w];
 			const u32 c0 = sum & 0xffffu, c1 = sum >> 16;
+			{
+				/* the tile's heaviest digit, (count << 8) | digit: selects the skew paths of the
+				 * placement below and of the next tile's count */
+				u32 top = c1 > c0 ? ((c1 << 8) | (u32) (2 * tid + 1)) : ((c0 << 8) | (u32) (2 * tid));
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+				if (lane == 0) s_misc[12 + warp] = top;
+			}
 			st_relaxed(agg + (size_t) cur * RADIX + 2 * tid, (LbT) (PPWord<LbT>::VALID | (LbT) c0));
 			st_relaxed(agg + (size_t) cur * RADIX + 2 * tid + 1, (LbT) (PPWord<LbT>::VALID | (LbT) c1));
 			const u32 pair = c0 + c1;
@@ -431,6 +492,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			u32 off = 0;
 #pragma unroll
 			for (int w = 0; w < DT / 32; ++w) if (w < warp) off += s_misc[w];
+			if (tid == 0) s_misc[16] = max(max(s_misc[12], s_misc[13]), max(s_misc[14], s_misc[15]));
 			const u32 ds0 = off + incl - pair, ds1 = ds0 + c0;
 			*reinterpret_cast<uint2*>(s_ds + s0 * RADIX + 2 * tid) = make_uint2(ds0, ds1);
 			u32 run = ds0 | (ds1 << 16);
@@ -454,6 +516,9 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		mark(3);
 		const u32 nxt2 = s_misc[8];
 		const bool more = nxt < num_tiles;
+		heavy = (s_misc[16] >> 8) >= (u32) (TILE / 8);
+		lumpy = (s_misc[16] >> 8) >= (u32) (TILE / 64);
+		heavy_digit = s_misc[16] & 0xffu;
 		if (nxt2 < num_tiles) {
 			/* the tile after next -> L2 (one 128-byte line per thread) */
 			const size_t lo = (size_t) nxt2 * TILE * sizeof(ElemT) + (size_t) tid * 128;
@@ -471,12 +536,40 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			u32* svals = buf_vals(b);
 			unsigned short* sinfo = buf_info(b);
 			const bool next_full = more && tile_count_of(nxt) == (u32) TILE;
-			if (cnt == (u32) TILE && next_full) {
+			if (cnt == (u32) TILE && skew_mode(heavy, lumpy)) {
+				/* skew path: keys of the candidate digits take their slots from a ballot and a
+				 * warp-private running base; the rest as usual.  (The next tile is loaded after
+				 * the loop: refilling a register right behind a ballot made ptxas wait for each load.) */
+				u32 h1, h2;
+				skew_candidates(heavy, heavy_digit, h1, h2);
+				u32 b1 = h1 < 0x100u ? ((wh[h1 >> 1] >> ((h1 & 1u) << 4)) & 0xffffu) : 0u;
+				u32 b2 = (wh[h2 >> 1] >> ((h2 & 1u) << 4)) & 0xffffu;
+				const u32 lt = lanemask_lt();
+#pragma unroll
+				for (int i = 0; i < IPT; ++i) {
+					const u32 d = v6_digit<ElemT>(key[i], start_bit, dmask);
+					const u32 m1 = __ballot_sync(0xffffffffu, d == h1), m2 = __ballot_sync(0xffffffffu, d == h2);
+					u32 p;
+					if (d == h1) p = b1 + __popc(m1 & lt);
+					else if (d == h2) p = b2 + __popc(m2 & lt);
+					else p = row_take(d);
+					b1 += __popc(m1); b2 += __popc(m2);
+					p = sw(p);
+					skeys[p] = key[i];
+					if (HAS_VAL) {
+						svals[p] = val[i];
+						sinfo[p] = (unsigned short) (wbase + i * 32u);
+					}
+				}
+				__syncwarp();
+				zero_row();
+				if (more) load_tile(nxt);
+			} else if (cnt == (u32) TILE && next_full) {
 				const ElemT* np = in + (size_t) nxt * TILE + wbase;
 				const u32* npv = vin + (size_t) nxt * TILE + wbase;
 #pragma unroll
 				for (int i = 0; i < IPT; ++i) {
-					const u32 p = row_take(v6_digit<ElemT>(key[i], start_bit, dmask));
+					const u32 p = sw(row_take(v6_digit<ElemT>(key[i], start_bit, dmask)));
 					skeys[p] = key[i];
 					key[i] = __ldcs(np + i * 32);
 					if (HAS_VAL) {
@@ -491,7 +584,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 #pragma unroll
 				for (int i = 0; i < IPT; ++i)
 					if (wbase + i * 32u < cnt) {
-						const u32 p = row_take(v6_digit<ElemT>(key[i], start_bit, dmask));
+						const u32 p = sw(row_take(v6_digit<ElemT>(key[i], start_bit, dmask)));
 						skeys[p] = key[i];
 						if (HAS_VAL) {
 							svals[p] = val[i];
@@ -554,7 +647,7 @@ __global__ void clo_radix_atomic_order_selftest_kernel(u32* __restrict__ out, u3
 
 template <typename ElemT, int THREADS, int IPT, typename LbT, bool HAS_VAL = false>
 constexpr size_t onesweep_v6_smem() {
-	constexpr size_t worker = (size_t) (THREADS / 32) * (RADIX / 2) * 4 + 4 * RADIX * 4 + 2 * RADIX * 8 + 16 * 4 +
+	constexpr size_t worker = (size_t) (THREADS / 32) * (RADIX / 2) * 4 + 4 * RADIX * 4 + 2 * RADIX * 8 + 32 * 4 +
 		2 * ((size_t) THREADS * IPT * sizeof(ElemT) + (HAS_VAL ? (size_t) THREADS * IPT * 6 : 0));
 	constexpr size_t prop = pp_propagate2_smem<LbT, THREADS, v6_prop_groups(THREADS, (int) sizeof(LbT))>();
 	return worker > prop ? worker : prop;

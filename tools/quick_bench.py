@@ -65,6 +65,16 @@ def main():
         n = 1 << args.log2n_sort
         os.environ["CLO_RADIX_PROFILE"] = "1"
         t_in = torch.randint(-2**31, 2**31 - 1, (n,), dtype=torch.int32, device="cuda")
+        dist = os.environ.get("QB_DIST", "uniform")
+        if dist == "zipf":
+            u = torch.rand(n, device="cuda", dtype=torch.float64)
+            rank = torch.exp(u * float(np.log(1 << 20))).to(torch.int64).clamp_(1, 1 << 20)
+            t_in = ((rank * 2654435761) & 0xFFFFFFFF).to(torch.int32)
+            del u, rank
+        elif dist == "sorted":
+            t_in = torch.arange(n, dtype=torch.int32, device="cuda")
+        elif dist == "v16":
+            t_in = torch.randint(0, 16, (n,), device="cuda", dtype=torch.int32) * 0x01010101
         t_out = torch.empty_like(t_in)
         b_in, b_out = clo.Buffer.wrap_tensor(ctx, t_in), clo.Buffer.wrap_tensor(ctx, t_out)
         s = clo.CloSort("satradix", ctx, clo.UINT)

@@ -24,7 +24,10 @@ del u, rank
 s = clo.CloSort("satradix", ctx, clo.UINT)
 out = torch.empty(n, dtype=torch.int32, device="cuda")
 bo = clo.Buffer.wrap_tensor(ctx, out)
+only = os.environ.get("CASES")
 for name, t in cases.items():
+    if only and not any(name.startswith(c) for c in only.split(",")):
+        continue
     bi = clo.Buffer.wrap_tensor(ctx, t)
     for _ in range(2):
         s.with_device_data(q, bi, bo, n)
@@ -38,5 +41,11 @@ for name, t in cases.items():
     uo = out.to(torch.int64) & 0xFFFFFFFF
     ok = bool((uo[1:] >= uo[:-1]).all().item())
     d = s.debug(q)
-    print(json.dumps({"keys": name, "ms": round(ms, 3), "gkeys": round(n / ms / 1e6, 1), "sorted": ok, "repaired": d[1], "timeout": d[0]}), flush=True)
+    s.set_timing(True)
+    s.with_device_data(q, bi, bo, n)
+    torch.cuda.synchronize()
+    tm = [round(x, 3) for x in s.get_timing()]
+    s.set_timing(False)
+    print(json.dumps({"keys": name, "ms": round(ms, 3), "gkeys": round(n / ms / 1e6, 1), "sorted": ok, "repaired": d[1], "timeout": d[0],
+                      "kernel_ms": tm}), flush=True)
     bi.destroy(); del uo
