@@ -36,6 +36,9 @@ int g_pp_flags = 0;
 
 #include "radix_prop.cuh"
 const int MAX_PASSES = 8;
+#ifndef CLO_IPT_U32
+#define CLO_IPT_U32 16
+#endif
 const int LB_FIRST = 4;     /* look-back window: first load batch */
 const int LB_NEXT = 4;      /* ... and the following ones */
 
@@ -526,6 +529,11 @@ struct CloRadixState {
 	int rank_atomic = 1;     /* CLO_RADIX_RANK=ballot selects the ballot ranks */
 	int cfg = 0;
 	/* optional per-kernel timing of the last call (clo_radix_set_timing) */
+	/* sticky status of the last call: the device flag is copied to pinned host memory behind every
+	 * call (no synchronisation); the next call looks at it once that copy has completed */
+	int* h_status = nullptr;
+	cudaEvent_t status_evt = nullptr;
+	bool status_pending = false;
 	int timing = 0;
 	int n_marks = 0;
 	cudaEvent_t marks[2 + MAX_PASSES + 2] = {};
@@ -569,6 +577,8 @@ int clo_radix_get_timing(CloRadixState* st, float* out, int cap) {
 
 void clo_radix_state_free(CloRadixState* st) {
 	if (!st) return;
+	if (st->h_status) cudaFreeHost(st->h_status);
+	if (st->status_evt) cudaEventDestroy(st->status_evt);
 	for (cudaEvent_t e : st->marks) if (e) cudaEventDestroy(e);
 	st->aux_keys.release(); st->aux_vals.release(); st->work.release(); st->pp.release();
 	delete st;
@@ -591,6 +601,13 @@ int clo_radix_status(CloRadixState* st, cudaStream_t stream) {
 	int flag = 0;
 	if (cudaMemcpyAsync(&flag, st->work.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess) return -1;
 	if (cudaStreamSynchronize(stream) != cudaSuccess) return -1;
+	if (flag != 0) {
+		/* reported now: do not report it again on the next call, and start from clean words */
+		if (st->pp.ptr) cudaMemsetAsync(st->pp.ptr, 0, st->pp.size, stream);
+		cudaMemsetAsync(st->work.ptr, 0, sizeof(int), stream);
+		if (st->h_status) *st->h_status = 0;
+		st->status_pending = false;
+	}
 	return flag;
 }
 
@@ -810,7 +827,7 @@ cudaError_t radix_sort_typed<u32, false, true>(CloRadixState* st, int sm_count, 
 		const u32* src, u32* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
 	if (st->cfg == 1)
 		return radix_sort_cfg<u32, false, true, 256, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
-	return radix_sort_cfg<u32, false, true, 512, 16>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
+	return radix_sort_cfg<u32, false, true, 512, CLO_IPT_U32>(st, sm_count, ks, sorted_bits, src, dst, vsrc, vdst, n, stream);
 }
 
 template <typename ElemT>
@@ -834,13 +851,35 @@ cudaError_t clo_radix_sort(CloRadixState* st, int sm_count, size_t elem_size, co
 	if (n >= (1ull << 40)) { if (err_msg) *err_msg = "radix sort: too many elements"; return cudaErrorInvalidValue; }
 	if (sorted_bits == 0 || sorted_bits > 64) { if (err_msg) *err_msg = "radix sort: invalid number of key bits"; return cudaErrorInvalidValue; }
 	if (payload_src && elem_size < 4) { if (err_msg) *err_msg = "radix sort: payload needs 4- or 8-byte keys"; return cudaErrorInvalidValue; }
+	/* A pass that ran into a look-back / propagator timeout (a grid that was not fully resident)
+	 * leaves wrong output and stale AGG / PREF words.  Callers of the device-data entry points never
+	 * synchronise, so the flag of the PREVIOUS call is reported here: that call's output is invalid. */
+	if (st->status_pending && cudaEventQuery(st->status_evt) == cudaSuccess) {
+		st->status_pending = false;
+		if (*st->h_status != 0) {
+			*st->h_status = 0;
+			if (st->pp.ptr) cudaMemsetAsync(st->pp.ptr, 0, st->pp.size, stream);
+			if (err_msg) *err_msg = "radix sort: the previous sort on this sorter timed out waiting for tile prefixes; its output is invalid";
+			return cudaErrorLaunchFailure;
+		}
+	}
+	cudaError_t rc;
 	switch (elem_size) {
-	case 1: return radix_sort_elem<unsigned char>(st, sm_count, ks, sorted_bits, src, dst, nullptr, nullptr, n, stream);
-	case 2: return radix_sort_elem<unsigned short>(st, sm_count, ks, sorted_bits, src, dst, nullptr, nullptr, n, stream);
-	case 4: return radix_sort_elem<u32>(st, sm_count, ks, sorted_bits, src, dst, payload_src, payload_dst, n, stream);
-	case 8: return radix_sort_elem<u64>(st, sm_count, ks, sorted_bits, src, dst, payload_src, payload_dst, n, stream);
+	case 1: rc = radix_sort_elem<unsigned char>(st, sm_count, ks, sorted_bits, src, dst, nullptr, nullptr, n, stream); break;
+	case 2: rc = radix_sort_elem<unsigned short>(st, sm_count, ks, sorted_bits, src, dst, nullptr, nullptr, n, stream); break;
+	case 4: rc = radix_sort_elem<u32>(st, sm_count, ks, sorted_bits, src, dst, payload_src, payload_dst, n, stream); break;
+	case 8: rc = radix_sort_elem<u64>(st, sm_count, ks, sorted_bits, src, dst, payload_src, payload_dst, n, stream); break;
 	default: if (err_msg) *err_msg = "radix sort: unsupported element size"; return cudaErrorInvalidValue;
 	}
+	if (rc == cudaSuccess && st->work.ptr) {
+		if (!st->h_status && cudaMallocHost((void**) &st->h_status, sizeof(int)) == cudaSuccess) *st->h_status = 0;
+		if (!st->status_evt) cudaEventCreateWithFlags(&st->status_evt, cudaEventDisableTiming);
+		if (st->h_status && st->status_evt && !st->status_pending &&
+			cudaMemcpyAsync(st->h_status, st->work.ptr, sizeof(int), cudaMemcpyDeviceToHost, stream) == cudaSuccess &&
+			cudaEventRecord(st->status_evt, stream) == cudaSuccess)
+			st->status_pending = true;
+	}
+	return rc;
 }
 
 /* ------------------------------------------------------------- partition */

@@ -11,6 +11,9 @@
 #include <cstdlib>
 
 using namespace clo;
+#ifndef CLO_IPT_U32
+#define CLO_IPT_U32 16
+#endif
 
 namespace {
 #include "radix_prop.cuh"
@@ -90,7 +93,7 @@ cudaError_t clo_radix_v6_pass(int elem_size, int wide, int tile, const void* in,
 		ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream) \
 	: launch_v6<ET, LT, 512, IPT_, HV, false>(tile, (const ET*) in, (ET*) out, vin, vout, n, (LT*) agg, (LT*) pref, \
 		ticket, bins, start_bit, dmask, err, sm_count, prof_on, flags, stream))
-	if (elem_size == 4 && !vin) return wide ? CLO_V6_GO(u32, u64, 16, false) : CLO_V6_GO(u32, u32, 16, false);
+	if (elem_size == 4 && !vin) return wide ? CLO_V6_GO(u32, u64, CLO_IPT_U32, false) : CLO_V6_GO(u32, u32, CLO_IPT_U32, false);
 	if (elem_size == 8 && !vin) return wide ? CLO_V6_GO(u64, u64, 10, false) : CLO_V6_GO(u64, u32, 10, false);
 	if (elem_size == 4 && vin) return wide ? CLO_V6_GO(u32, u64, 8, true) : CLO_V6_GO(u32, u32, 8, true);
 	if (elem_size == 8 && vin) return wide ? CLO_V6_GO(u64, u64, 6, true) : CLO_V6_GO(u64, u32, 6, true);

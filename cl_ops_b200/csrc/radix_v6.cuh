@@ -405,6 +405,9 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			goff_of(gslot), s_ds + dslot * RADIX, start_bit, dmask, err_flag);
 	};
 
+	/* test hook: pretend a prefix wait timed out, so the status reporting of the host side can be
+	 * exercised (tests/test_gpu_sort.py::test_satradix_timeout_is_reported) */
+	if ((flags & 64) && blockIdx.x == V6_NUM_PROP && tid == 0) atomicExch(err_flag, 1);
 	/* ---- prologue: two tickets (the next tile is always known one iteration ahead) */
 	if (tid == 0) { s_misc[8] = atomicAdd(ticket, 1u); s_misc[9] = atomicAdd(ticket, 1u); s_misc[10] = 0; s_misc[11] = 0; }
 	zero_row();

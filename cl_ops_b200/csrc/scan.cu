@@ -352,13 +352,20 @@ cudaError_t launch_scan_pp(ScanState& st, const void* in, void* out, size_t n, c
 	u64* pref = agg + st.pp_tiles_cap * 2;
 	if ((e = cudaMemsetAsync(ticket, 0, sizeof(u32), stream)) != cudaSuccess) return e;
 	auto kern = clo_scan_pp<ElemT, SumT, THREADS, VPT, AHEAD, LAG>;
-	static int ctas_per_sm = 0;
-	if (!ctas_per_sm) {
+	/* the shared-memory opt-in and the occupancy are per-device state */
+	static bool configured[64] = {};
+	static int ctas_per_sm_dev[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) dev = 0;
+	if (!configured[dev]) {
 		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
 		int k = 0;
 		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kern, THREADS, SMEM) != cudaSuccess || k < 1) k = 1;
-		ctas_per_sm = k;
+		ctas_per_sm_dev[dev] = k;
+		configured[dev] = true;
 	}
+	const int ctas_per_sm = ctas_per_sm_dev[dev];
 	size_t workers = (size_t) sms * ctas_per_sm - 1;
 	if (workers > tiles) workers = tiles;
 	kern<<<(unsigned) (1 + workers), THREADS, SMEM, stream>>>((const ElemT*) in, (SumT*) out, n, (u32) tiles,

@@ -243,11 +243,16 @@ extern "C" CCLContext* ccl_queue_get_context(CCLQueue* cq, GError** err) { (void
 static const size_t CLO_EVENT_LOG_CAP = 64;
 
 ccl_event* clo_queue_begin(ccl_queue* cq, const char* name) {
-	if (!cq->profiling && cq->events.size() >= CLO_EVENT_LOG_CAP) {
-		/* recycle the oldest half; callers only ever hold the latest event */
-		size_t drop = cq->events.size() / 2;
-		for (size_t i = 0; i < drop; ++i) free_event(cq->events[i]);
-		cq->events.erase(cq->events.begin(), cq->events.begin() + drop);
+	if (!cq->profiling && cq->events.size() >= CLO_EVENT_LOG_CAP && (cq->events.size() % CLO_EVENT_LOG_CAP) == 0) {
+		/* Every CCLEvent stays a valid handle until ccl_queue_gc / ccl_queue_destroy, as in cf4ocl
+		 * (a client may keep old events in wait lists).  What is given back early is only the CUDA
+		 * event of entries that have already completed: an entry without one reads as signalled
+		 * (ccl_event_wait and the wait lists skip it). */
+		for (ccl_event* old : cq->events)
+			if (old->end && cudaEventQuery(old->end) == cudaSuccess) {
+				cudaEventDestroy(old->end);
+				old->end = nullptr;
+			}
 	}
 	ccl_event* e = new ccl_event();
 	e->start = nullptr; e->end = nullptr; e->cq = cq;

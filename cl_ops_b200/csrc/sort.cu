@@ -197,7 +197,10 @@ static CCLEvent* satradix_sort_with_device_data(CloSort* sorter, CCLQueue* cq_ex
 		clo_type_sizeof(sorter->elem_type), sorter->ks, bits, data_in->ptr, dst, NULL, NULL,
 		numel, cq_exec->stream, &msg);
 	clo_queue_end(cq_exec, evt);
-	if (rc != cudaSuccess && msg) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg); return NULL; }
+	if (rc != cudaSuccess && msg) {
+		g_set_error(err, CLO_ERROR, rc == cudaErrorLaunchFailure ? CLO_ERROR_LIBRARY : CLO_ERROR_ARGS, "%s", msg);
+		return NULL;
+	}
 	if (clo_cuda_failed(rc, err, "clo_radix_sort")) return NULL;
 	return evt;
 }
