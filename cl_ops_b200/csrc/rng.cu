@@ -241,7 +241,8 @@ const GenFn kGen[R_COUNT] = { launch_generate<0>, launch_generate<1>, launch_gen
 /* ------------------------------------------------------------- sources */
 /* CUDA device source of each generator, the analogue of the OpenCL source the
  * reference hands to its clients (clo_rng.c:371-372): clo_statetype,
- * clo_rng_next(states, index) and the next_int API of clo_rng_api.cl:33-105. */
+ * clo_rng_next(states, index) and the next_int{,2,4,8} API of clo_rng_api.cl:33-105
+ * (work-item k of a vector call uses the streams gid + k * global_size, clo_rng_workitem.cl:24-32). */
 
 #define CLO_SRC_API \
 	"__device__ inline unsigned clo_rng_next_int(clo_statetype* states, unsigned n) {\n" \
@@ -253,7 +254,16 @@ const GenFn kGen[R_COUNT] = { launch_generate<0>, launch_generate<1>, launch_gen
 	"__device__ inline uint4 clo_rng_next_int4(clo_statetype* states, unsigned n) {\n" \
 	"\tunsigned g = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;\n" \
 	"\treturn make_uint4(clo_rng_next(states, g) % n, clo_rng_next(states, gs + g) % n,\n" \
-	"\t\tclo_rng_next(states, 2 * gs + g) % n, clo_rng_next(states, 3 * gs + g) % n);\n}\n"
+	"\t\tclo_rng_next(states, 2 * gs + g) % n, clo_rng_next(states, 3 * gs + g) % n);\n}\n" \
+	"struct uint8 { unsigned s0, s1, s2, s3, s4, s5, s6, s7; };\n" \
+	"__device__ inline uint8 clo_rng_next_int8(clo_statetype* states, unsigned n) {\n" \
+	"\tunsigned g = blockIdx.x * blockDim.x + threadIdx.x, gs = gridDim.x * blockDim.x;\n" \
+	"\tuint8 r;\n" \
+	"\tr.s0 = clo_rng_next(states, g) % n; r.s1 = clo_rng_next(states, gs + g) % n;\n" \
+	"\tr.s2 = clo_rng_next(states, 2 * gs + g) % n; r.s3 = clo_rng_next(states, 3 * gs + g) % n;\n" \
+	"\tr.s4 = clo_rng_next(states, 4 * gs + g) % n; r.s5 = clo_rng_next(states, 5 * gs + g) % n;\n" \
+	"\tr.s6 = clo_rng_next(states, 6 * gs + g) % n; r.s7 = clo_rng_next(states, 7 * gs + g) % n;\n" \
+	"\treturn r;\n}\n"
 
 const char kSrcLcg[] =
 	"typedef unsigned long long clo_statetype;\n"

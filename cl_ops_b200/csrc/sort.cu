@@ -21,7 +21,7 @@ struct clo_sort {
 	/* backend */
 	CloKeySpec ks;
 	unsigned radix;          /* satradix "radix=" option (clo_sort_satradix.c:352,385-392) */
-	unsigned minps, maxps, maxsfs;  /* abitonic options, kept as hints */
+	unsigned minps, maxps, maxsfs;  /* abitonic options: maxps / maxsfs set the fusion depth of the bitonic kernel */
 	CloRadixState* rs;
 	CloBitonicState* bs;
 	CloJitSort* jit;         /* run-time compiled network for compare / get_key strings outside the menu */
@@ -297,20 +297,26 @@ static CCLEvent* bitonic_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exe
 	return evt;
 }
 
-static const char* const kBitonicKernels[] = { "clo_bitonic_local", "clo_bitonic_global" };
+static const char* const kBitonicKernels[] = { "clo_bitonic_fused", "clo_bitonic_local", "clo_bitonic_global" };
 
-static cl_uint bitonic_get_num_kernels(CloSort* s, GError** err) { (void) s; (void) err; return 2; }
+static cl_uint bitonic_get_num_kernels(CloSort* s, GError** err) { (void) s; (void) err; return 3; }
 
 static const char* bitonic_get_kernel_name(CloSort* s, cl_uint i, GError** err) {
 	(void) s;
-	if (i >= 2) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
+	if (i >= 3) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
 	return kBitonicKernels[i];
 }
 
+/* shared memory of the kernels above: the fused kernel's padded tile (8192 elements of up to
+ * 4 bytes, 4096 of 8 bytes, one padding element per 32); the padded-N kernels' 4096-element tile
+ * plus its flag bytes; the global step uses none */
 static size_t bitonic_get_localmem_usage(CloSort* s, cl_uint i, size_t lws_max, size_t numel, GError** err) {
 	(void) lws_max; (void) numel;
-	if (i >= 2) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
-	return i == 0 ? 4096 * clo_type_sizeof(s->elem_type) : 0;
+	if (i >= 3) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
+	const size_t es = clo_type_sizeof(s->elem_type);
+	const size_t tile = es == 8 ? 4096 : 8192;
+	if (i == 0) return (tile + tile / 32 + 1) * es;
+	return i == 1 ? 4096 * es + 4096 : 0;
 }
 
 extern "C" const CloSortImplDef clo_sort_sbitonic_def = {
@@ -413,6 +419,10 @@ extern "C" CloSort* clo_sort_new(const char* type, const char* options, CCLConte
 	GError* ierr = NULL;
 	uint32_t shift = 0; uint64_t mask = ~0ull; int desc = 0;
 	s->impl_def.init(s, options, &ierr);
+	/* abitonic's tuning options are real knobs here: steps fused in registers (maxps) and steps
+	 * taken in the shared-memory tile (maxsfs) -- clo_sort_abitonic.c:486-542 */
+	if (!ierr && def == &clo_sort_abitonic_def)
+		clo_bitonic_set_fusion(s->bs, (int) s->maxps, s->maxsfs > 13u ? 13 : (int) s->maxsfs);
 	const bool in_menu = parse_get_key(get_key, shift, mask) && parse_compare(compare, desc);
 	const bool comparison_sort = def != &clo_sort_satradix_def;
 	if (!ierr && !in_menu && comparison_sort) {

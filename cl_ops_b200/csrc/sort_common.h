@@ -99,6 +99,9 @@ CloBitonicState* clo_bitonic_state_new();
 void clo_bitonic_state_free(CloBitonicState* st);
 cudaError_t clo_bitonic_sort(CloBitonicState* st, size_t elem_size, const CloKeySpec& ks,
 	void* data, size_t n, cudaStream_t stream);
+/* abitonic's tuning options: steps fused in registers (maxps, 1..4) and the largest number of
+ * steps taken in shared memory (maxsfs; 13 = the full 8192-element tile) */
+void clo_bitonic_set_fusion(CloBitonicState* st, int max_private_steps, int max_local_steps);
 cudaError_t clo_gselect_sort(size_t elem_size, const CloKeySpec& ks, const void* in, void* out,
 	size_t n, cudaStream_t stream);
 

@@ -114,3 +114,67 @@ def test_custom_seed_hash_strings_are_compiled_at_run_time(clo, ctx, queue):
     with pytest.raises(clo.CloError) as ei:
         clo.CloRng("lcg", ctx, clo.SEED_DEV_GID, None, 16, 0, "x = x +* 2", queue)
     assert ei.value.code == clo.CLO_ERROR_ARGS and "does not compile" in str(ei.value)
+
+
+@pytest.mark.parametrize("rng", ["lcg", "xorshift128", "mwc64x", "tauslcg"])
+def test_next_int_vector_api_through_the_program_shim(clo, ctx, queue, rng):
+    """clo_rng_next_int{,2,4,8} (clo_rng_api.cl:33-105): a client kernel appended to
+    clo_rng_get_source(), built and launched through the cf4ocl-style program/kernel shim (as
+    clo_rng_bench.c:176-312 does).  Work-item g of a width-W call draws from the streams
+    g + k * global_size, k < W (clo_rng_workitem.cl:24-32); every lane must match the oracle."""
+    import ctypes
+    L = clo.lib()
+    vp = ctypes.c_void_p
+    L.ccl_program_new_from_source.restype = vp
+    L.ccl_program_new_from_source.argtypes = [vp, ctypes.c_char_p, vp]
+    L.ccl_program_build.restype = ctypes.c_int
+    L.ccl_program_build.argtypes = [vp, ctypes.c_char_p, vp]
+    L.ccl_program_get_kernel.restype = vp
+    L.ccl_program_get_kernel.argtypes = [vp, ctypes.c_char_p, vp]
+    L.ccl_program_destroy.argtypes = [vp]
+    L.ccl_arg_new.restype = vp
+    L.ccl_arg_new.argtypes = [vp, ctypes.c_size_t]
+    L.ccl_kernel_enqueue_ndrange.restype = vp
+    L.ccl_kernel_enqueue_ndrange.argtypes = [vp, vp, ctypes.c_uint, vp, vp, vp, vp, vp]
+    gs, n = 1024, 1000
+    r = clo.CloRng(rng, ctx, clo.SEED_DEV_GID, None, 8 * gs, 42, "KNUTH(x)", queue)
+    kernels = """
+__kernel void k1(__global clo_statetype* st, __global uint* out, uint n) { out[get_global_id(0)] = clo_rng_next_int(st, n); }
+__kernel void k2(__global clo_statetype* st, __global uint* out, uint n) {
+	uint g = get_global_id(0), gs = get_global_size(0); uint2 v = clo_rng_next_int2(st, n); out[g] = v.x; out[gs + g] = v.y; }
+__kernel void k4(__global clo_statetype* st, __global uint* out, uint n) {
+	uint g = get_global_id(0), gs = get_global_size(0); uint4 v = clo_rng_next_int4(st, n);
+	out[g] = v.x; out[gs + g] = v.y; out[2 * gs + g] = v.z; out[3 * gs + g] = v.w; }
+__kernel void k8(__global clo_statetype* st, __global uint* out, uint n) {
+	uint g = get_global_id(0), gs = get_global_size(0); uint8 v = clo_rng_next_int8(st, n);
+	out[g] = v.s0; out[gs + g] = v.s1; out[2 * gs + g] = v.s2; out[3 * gs + g] = v.s3;
+	out[4 * gs + g] = v.s4; out[5 * gs + g] = v.s5; out[6 * gs + g] = v.s6; out[7 * gs + g] = v.s7; }
+"""
+    err = clo._Err()
+    prg = L.ccl_program_new_from_source(ctx.h, (r.get_source() + kernels).encode(), err.ref())
+    err.check()
+    assert L.ccl_program_build(prg, None, err.ref())
+    err.check()
+    states = oracle.rng_seeds_dev_gid(rng, 1, 42, 8 * gs)
+    seeds_dev = vp(L.clo_rng_get_device_seeds(r.h))
+    out = clo.Buffer(ctx, size=8 * gs * 4)
+    for name, width in (("k1", 1), ("k2", 2), ("k4", 4), ("k8", 8)):
+        k = L.ccl_program_get_kernel(prg, name.encode(), err.ref())
+        err.check()
+        nn = ctypes.c_uint(n)
+        L.ccl_kernel_set_args(vp(k), seeds_dev, vp(out.h), vp(L.ccl_arg_new(ctypes.byref(nn), 4)), vp(None))
+        g, l = ctypes.c_size_t(gs), ctypes.c_size_t(128)
+        L.ccl_kernel_enqueue_ndrange(k, queue.h, 1, None, ctypes.byref(g), ctypes.byref(l), None, err.ref())
+        err.check()
+        got = out.read(queue, np.uint32, width * gs)
+        want, states = oracle.rng_generate(rng, states, 8 * gs, 1, maxint=n)
+        want = np.asarray(want).reshape(-1)
+        assert np.array_equal(got, want[: width * gs]), name
+        # streams beyond the call's width did not advance: restore them for the next comparison
+        st_dev = r.read_seeds(queue)
+        assert np.array_equal(st_dev.view(np.uint8).reshape(8 * gs, -1)[: width * gs],
+                              np.asarray(states).view(np.uint8).reshape(8 * gs, -1)[: width * gs])
+        states = st_dev
+    out.destroy()
+    L.ccl_program_destroy(prg)
+    r.destroy()
