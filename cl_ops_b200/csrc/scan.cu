@@ -571,22 +571,28 @@ static CCLEvent* blelloch_scan_with_device_data(CloScan* scanner, CCLQueue* cq_e
 	return scan_device(scanner, cq_exec, data_in, data_out, NULL, numel, err);
 }
 
-static const char* const kScanKernels[] = { "clo_scan_lookback" };
+static const char* const kScanKernels[] = { "clo_scan_pp", "clo_scan_lookback", "clo_scan_reduce_partial", "clo_scan_reduce_final" };
 
-static cl_uint blelloch_get_num_kernels(CloScan* scanner, GError** err) { (void) scanner; (void) err; return 1; }
+static cl_uint blelloch_get_num_kernels(CloScan* scanner, GError** err) { (void) scanner; (void) err; return 4; }
 
 static const char* blelloch_get_kernel_name(CloScan* scanner, cl_uint i, GError** err) {
 	(void) scanner;
-	if (i >= 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
+	if (i >= 4) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
 	return kScanKernels[i];
 }
 
 static size_t blelloch_get_localmem_usage(CloScan* scanner, cl_uint i, size_t lws_max, size_t numel, GError** err) {
 	(void) lws_max; (void) numel;
-	if (i >= 1) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
-	/* s_tile + per-warp totals + tile prefix */
+	if (i >= 4) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
 	const size_t acc = clo_type_sizeof(scanner->sum_type) == 8 || scanner->sum_type >= CLO_FLOAT ? 8 : 4;
-	return 8 + (SCAN_THREADS / 32 + 1) * acc;
+	if (i == 0) {
+		/* clo_scan_pp: ring of AHEAD + 1 + LAG tiles of 256 threads x 4 vectors of 16 bytes, the
+		 * per-slot warp totals and the ticket ring */
+		const size_t slots = SPP_AHEAD + 1 + SPP_LAG;
+		return slots * (size_t) SPP_THREADS * SPP_VPT * 16 + slots * (SPP_THREADS / 32) * acc + (slots + 2) * 4;
+	}
+	if (i == 1) return 8 + (SCAN_THREADS / 32 + 1) * acc;       /* clo_scan_lookback: tile id + warp totals + tile prefix */
+	return i == 2 ? 8 * acc : 0;                                   /* clo_scan_reduce_partial: warp totals */
 }
 
 extern "C" const CloScanImplDef clo_scan_blelloch_def = {

@@ -205,7 +205,7 @@ static CCLEvent* satradix_sort_with_device_data(CloSort* sorter, CCLQueue* cq_ex
 	return evt;
 }
 
-static const char* const kSatradixKernels[] = { "clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep" };
+static const char* const kSatradixKernels[] = { "clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep_v6" };
 
 static cl_uint satradix_get_num_kernels(CloSort* s, GError** err) { (void) s; (void) err; return 3; }
 
@@ -217,11 +217,19 @@ static const char* satradix_get_kernel_name(CloSort* s, cl_uint i, GError** err)
 
 static size_t satradix_get_localmem_usage(CloSort* s, cl_uint i, size_t lws_max, size_t numel, GError** err) {
 	(void) lws_max; (void) numel;
+	/* shared memory of the kernels as launched for a keys-only sort of this element type:
+	 * histogram [passes][256 bins][columns] u32 (radix.cu launch_histogram); the bin scan's warp
+	 * totals; the onesweep pass' packed warp rows, digit-start / offset tables and its two staging
+	 * buffers of one tile each (radix_v6.cuh onesweep_v6_smem; 512 x 16 keys of 4 bytes, 512 x 10
+	 * of 8 bytes; narrower keys run the older pass with one staging buffer of 512 x 16 keys) */
 	const size_t es = clo_type_sizeof(s->elem_type);
+	const size_t passes = es;                          /* 8-bit digits */
 	switch (i) {
-	case 0: return 8 * 256 * 4;
+	case 0: return (passes <= 2 ? passes : (passes <= 4 ? 4 : 8)) * 256 * (passes <= 4 ? 32 : 16) * 4;
 	case 1: return 8 * 8;
-	case 2: return 16 * 256 * 4 + 256 * 4 + 256 * 8 + 64 + (size_t) 512 * (es == 8 ? 8 : 16) * es;
+	case 2:
+		if (es >= 4) return 16 * 128 * 4 + 4 * 256 * 4 + 2 * 256 * 8 + 32 * 4 + 2 * (size_t) 512 * (es == 8 ? 10 : 16) * es;
+		return 16 * 256 * 4 + 256 * 4 + 256 * 8 + 16 * 4 + (size_t) 512 * 16 * es;
 	default: g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0;
 	}
 }

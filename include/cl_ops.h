@@ -12,7 +12,12 @@ extern "C" {
 #include <cl_ops/clo_common.h>
 #include <cl_ops/clo_rng.h>
 #include <cl_ops/clo_sort_abstract.h>
+#include <cl_ops/clo_sort_abitonic.h>
+#include <cl_ops/clo_sort_sbitonic.h>
+#include <cl_ops/clo_sort_gselect.h>
+#include <cl_ops/clo_sort_satradix.h>
 #include <cl_ops/clo_scan_abstract.h>
+#include <cl_ops/clo_scan_blelloch.h>
 #include <cl_ops/clo_b200.h>
 
 #ifdef __cplusplus

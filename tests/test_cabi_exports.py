@@ -98,3 +98,18 @@ def test_product_has_no_cpu_fallback():
         if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
             text = open(path, errors="ignore").read()
             assert "import oracle" not in text and "liboracle" not in text and "clo_oracle" not in text, path
+
+
+@pytest.mark.parametrize("header", ["clo_sort_abitonic.h", "clo_sort_sbitonic.h", "clo_sort_gselect.h",
+                                    "clo_sort_satradix.h", "clo_scan_blelloch.h"])
+def test_per_algorithm_headers_compile_on_their_own(header, tmp_path):
+    """cl_ops.h:29-52 lists one public header per algorithm; a client may include one directly."""
+    import subprocess
+    src = tmp_path / "client.c"
+    macro = {"clo_sort_abitonic.h": "CLO_SORT_ABITONIC_NUM_KERNELS", "clo_sort_sbitonic.h": "CLO_SORT_SBITONIC_NUM_KERNELS",
+             "clo_sort_gselect.h": "CLO_SORT_GSELECT_NUM_KERNELS", "clo_sort_satradix.h": "CLO_SORT_SATRADIX_NUM_KERNELS",
+             "clo_scan_blelloch.h": "CLO_SCAN_BLELLOCH_NUM_KERNELS"}[header]
+    src.write_text("#include <cl_ops/%s>\nint n_kernels(void) { return %s; }\n" % (header, macro))
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        "-I", os.path.join(ROOT, "include", "compat"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

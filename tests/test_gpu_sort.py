@@ -427,3 +427,39 @@ def test_custom_macro_strings_gselect_and_errors(clo, ctx, queue):
     with pytest.raises(clo.CloError) as ei:
         clo.CloSort("satradix", ctx, oracle.UINT, get_key="((x) * 3)")
     assert ei.value.code == clo.CLO_ERROR_ARGS
+
+
+def test_introspection_getters_name_real_kernels(clo, ctx):
+    """clo_sort_get_kernel_name / clo_scan_get_kernel_name (clo_sort_abstract.c:571-629) return the
+    names of CUDA kernels that exist in the library, the counts of the per-algorithm headers, and
+    non-trivial shared-memory sizes."""
+    import ctypes, os, re
+    L = clo.lib()
+    blob = open(os.path.join(os.path.dirname(clo.__file__), "libcl_ops.so"), "rb").read()
+    hdr = os.path.join(os.path.dirname(os.path.dirname(clo.__file__)), "include", "cl_ops")
+    want = {"sbitonic": "CLO_SORT_SBITONIC_NUM_KERNELS", "abitonic": "CLO_SORT_ABITONIC_NUM_KERNELS",
+            "gselect": "CLO_SORT_GSELECT_NUM_KERNELS", "satradix": "CLO_SORT_SATRADIX_NUM_KERNELS"}
+    L.clo_sort_get_localmem_usage.restype = ctypes.c_size_t
+    for alg, macro in want.items():
+        text = open(os.path.join(hdr, "clo_sort_%s.h" % alg)).read()
+        n_hdr = int(re.search(r"#define\s+%s\s+(\d+)" % macro, text).group(1))
+        s = clo.CloSort(alg, ctx, clo.UINT)
+        names = s.kernel_names()
+        assert len(names) == n_hdr
+        for i, nm in enumerate(names):
+            assert nm.encode() in blob, "%s is not a kernel of the library" % nm
+            assert ('"%s"' % nm) in text, "%s is not named by clo_sort_%s.h" % (nm, alg)
+            e = clo._Err()
+            L.clo_sort_get_localmem_usage(s.h, i, 0, 1 << 20, e.ref())
+            e.check()
+        s.destroy()
+    sc = clo.CloScan("blelloch", ctx, clo.UINT, clo.UINT)
+    L.clo_scan_get_kernel_name.restype = ctypes.c_char_p
+    e = clo._Err()
+    n = L.clo_scan_get_num_kernels(sc.h, e.ref())
+    text = open(os.path.join(hdr, "clo_scan_blelloch.h")).read()
+    assert n == int(re.search(r"#define\s+CLO_SCAN_BLELLOCH_NUM_KERNELS\s+(\d+)", text).group(1))
+    for i in range(n):
+        nm = L.clo_scan_get_kernel_name(sc.h, i, e.ref())
+        assert nm in blob and ('"%s"' % nm.decode()) in text
+    sc.destroy()
