@@ -327,7 +327,7 @@ cudaError_t launch_scan(ScanState& st, const void* in, void* out, size_t n, cons
 /* persistent kernel (scan_pp.cuh): used for large, 16-byte aligned inputs of the hot type pairs */
 const size_t SPP_MIN_ELEMS = (size_t) 1 << 22;
 
-template <typename ElemT, typename SumT, int THREADS = SPP_THREADS, int VPT = SPP_VPT, int AHEAD = SPP_AHEAD, int LAG = SPP_LAG>
+template <typename ElemT, typename SumT, int THREADS = SPP_THREADS, int VPT = SPP_VPT, int AHEAD = SPP_AHEAD, int LAG = SPP_LAG, bool ONEBAR = false>
 cudaError_t launch_scan_pp(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) {
 	typedef typename AccOf<SumT>::type AccT;
 	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
@@ -351,7 +351,7 @@ cudaError_t launch_scan_pp(ScanState& st, const void* in, void* out, size_t n, c
 	u64* agg = (u64*) ((char*) st.pp.ptr + HDR_BYTES);
 	u64* pref = agg + st.pp_tiles_cap * 2;
 	if ((e = cudaMemsetAsync(ticket, 0, sizeof(u32), stream)) != cudaSuccess) return e;
-	auto kern = clo_scan_pp<ElemT, SumT, THREADS, VPT, AHEAD, LAG>;
+	auto kern = ONEBAR ? clo_scan_pp1b<ElemT, SumT, THREADS, VPT, AHEAD, LAG> : clo_scan_pp<ElemT, SumT, THREADS, VPT, AHEAD, LAG>;
 	/* the shared-memory opt-in and the occupancy are per-device state */
 	static bool configured[64] = {};
 	static int ctas_per_sm_dev[64] = {};
@@ -392,7 +392,7 @@ cudaError_t launch_scan<E, S>(ScanState& st, const void* in, void* out, size_t n
 CLO_SCAN_PP_PAIR(unsigned int, unsigned long long)
 CLO_SCAN_PP_PAIR(int, int)
 CLO_SCAN_PP_PAIR(int, long long)
-CLO_SCAN_PP_PAIR(float, float)
+
 CLO_SCAN_PP_PAIR(float, double)
 CLO_SCAN_PP_PAIR(unsigned long long, unsigned long long)
 CLO_SCAN_PP_PAIR(double, double)
@@ -409,6 +409,10 @@ cudaError_t launch_scan<unsigned int, unsigned int>(ScanState& st, const void* i
 		case 13: return launch_scan_pp<unsigned int, unsigned int, 128, 4, 1, 6>(st, in, out, n, carry, sms, stream);
 		case 14: return launch_scan_pp<unsigned int, unsigned int, 256, 3, 1, 6>(st, in, out, n, carry, sms, stream);
 		case 15: return launch_scan_pp<unsigned int, unsigned int, 512, 4, 1, 1>(st, in, out, n, carry, sms, stream);
+		case 20: return launch_scan_pp<unsigned int, unsigned int, 256, 4, 1, 4, true>(st, in, out, n, carry, sms, stream);
+		case 21: return launch_scan_pp<unsigned int, unsigned int, 256, 3, 1, 6, true>(st, in, out, n, carry, sms, stream);
+		case 22: return launch_scan_pp<unsigned int, unsigned int, 256, 4, 1, 5, true>(st, in, out, n, carry, sms, stream);
+		case 23: return launch_scan_pp<unsigned int, unsigned int, 128, 4, 1, 6, true>(st, in, out, n, carry, sms, stream);
 		default: return launch_scan_pp<unsigned int, unsigned int>(st, in, out, n, carry, sms, stream);
 		}
 	}
@@ -420,6 +424,29 @@ cudaError_t launch_scan<unsigned int, unsigned int>(ScanState& st, const void* i
 	case 5: return launch_scan_cfg<unsigned int, unsigned int, 128, 4, 16>(st, in, out, n, carry, stream);
 	default: return launch_scan_cfg<unsigned int, unsigned int, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream);
 	}
+}
+
+template <>
+cudaError_t launch_scan<float, float>(ScanState& st, const void* in, void* out, size_t n,
+		const void* carry, int sms, cudaStream_t stream) {
+	if (scan_pp_applicable<float, float>(st, in, out, n)) {
+		switch (st.cfg) {      /* CLO_SCAN_CFG 10..: shapes of the persistent kernel */
+		case 11: return launch_scan_pp<float, float, 512, 2, 1, 4>(st, in, out, n, carry, sms, stream);
+		case 12: return launch_scan_pp<float, float, 256, 2, 1, 8>(st, in, out, n, carry, sms, stream);
+		case 13: return launch_scan_pp<float, float, 128, 4, 1, 6>(st, in, out, n, carry, sms, stream);
+		case 14: return launch_scan_pp<float, float, 256, 3, 1, 6>(st, in, out, n, carry, sms, stream);
+		case 15: return launch_scan_pp<float, float, 512, 2, 2, 3>(st, in, out, n, carry, sms, stream);
+		case 16: return launch_scan_pp<float, float, 1024, 1, 1, 4>(st, in, out, n, carry, sms, stream);
+		case 20: return launch_scan_pp<float, float, 256, 4, 1, 4, true>(st, in, out, n, carry, sms, stream);
+		case 21: return launch_scan_pp<float, float, 256, 3, 1, 6, true>(st, in, out, n, carry, sms, stream);
+		case 22: return launch_scan_pp<float, float, 256, 4, 1, 5, true>(st, in, out, n, carry, sms, stream);
+		case 23: return launch_scan_pp<float, float, 128, 4, 1, 6, true>(st, in, out, n, carry, sms, stream);
+		case 24: return launch_scan_pp<float, float, 128, 4, 1, 4, true>(st, in, out, n, carry, sms, stream);
+		case 25: return launch_scan_pp<float, float, 256, 2, 1, 8, true>(st, in, out, n, carry, sms, stream);
+		default: return launch_scan_pp<float, float>(st, in, out, n, carry, sms, stream);
+		}
+	}
+	return launch_scan_cfg<float, float, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream);
 }
 
 template <typename ElemT, typename SumT>
@@ -638,6 +665,13 @@ extern "C" void clo_scan_destroy(CloScan* scan) {
 	scan->impl_def.finalize(scan);
 	{
 		CloDeviceGuard g(scan->ctx->dev.ordinal);
+		if (getenv("CLO_SCAN_STATS") && scan->st.pp.ptr) {
+			/* development aid: prefix-word polls of the persistent kernel since the scanner was made */
+			unsigned h[4] = {};
+			cudaDeviceSynchronize();
+			cudaMemcpy(h, scan->st.pp.ptr, sizeof(h), cudaMemcpyDeviceToHost);
+			fprintf(stderr, "clo_scan stats: err %u prefix polls %u\n", h[1], h[3]);
+		}
 		scan->st.scratch.release();
 		scan->st.partials.release();
 		scan->st.pp.release();

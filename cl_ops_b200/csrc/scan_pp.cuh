@@ -312,4 +312,182 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 	spp_cp_async_wait<0>();
 }
 
+/* ---- second schedule of the same pipeline: ONE CTA barrier per tile.
+ * ncu on the float instance of clo_scan_pp (profiles/r02_scan_pp_f32_ncu_summary.txt): 25 %
+ * occupancy, issue slots 32 % busy, 3.9 of 11 stall cycles per issue at the CTA barrier and 3.7
+ * on the short scoreboard -- a latency chain, not a bandwidth limit: three barriers per tile, the
+ * third one behind thread 0 polling the tile's prefix word.  Here
+ *   - the ticket of a tile is written to shared memory one iteration before it is read, and a
+ *     tile's warp sums are read one barrier after they were written, so one barrier per iteration
+ *     orders everything;
+ *   - every warp reads the tile's PREF word itself (lane 0 requests it before the reduce, polls
+ *     after it, broadcasts by shuffle): no warp waits for another warp's poll. */
+template <typename ElemT, typename SumT, int THREADS, int VPT_ = SPP_VPT, int AHEAD_ = SPP_AHEAD, int LAG_ = SPP_LAG>
+__global__ void __launch_bounds__(THREADS, 2)
+clo_scan_pp1b(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 num_tiles,
+		u64* __restrict__ agg, u64* __restrict__ pref, u32* __restrict__ ticket, u32 epoch,
+		const SumT* __restrict__ carry_in, int* __restrict__ err_flag) {
+	typedef typename AccOf<SumT>::type AccT;
+	typedef AccWords<AccT> AW;
+	typedef typename std::conditional<std::is_same<SumT, float>::value, float, AccT>::type IntraT;
+	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
+	constexpr int VB = EPV * (int) sizeof(ElemT);
+	static_assert(VB == 16, "the ring is filled with 16-byte cp.async");
+	static_assert(AHEAD_ >= 1, "a tile's warp sums must not be rewritten in the iteration after their last use");
+	constexpr int VPT = VPT_;
+	constexpr int WARPS = THREADS / 32;
+	constexpr int TILE = THREADS * VPT * EPV;
+	constexpr int S = AHEAD_ + 1 + LAG_;
+	constexpr int NT = S + 2;                                 /* ticket slots */
+	constexpr int OCH = (sizeof(SumT) * EPV <= 16) ? EPV : (16 / (int) sizeof(SumT));
+
+	const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
+	if (blockIdx.x == 0) {
+		spp_propagate<AccT, THREADS>(agg, pref, num_tiles, epoch, carry, err_flag);
+		return;
+	}
+
+	extern __shared__ __align__(16) unsigned char spp_smem[];
+	ElemT* ring = reinterpret_cast<ElemT*>(spp_smem);            /* [S][TILE] */
+	__shared__ u32 s_tile[NT];
+	__shared__ AccT s_wsum[2][WARPS];                             /* by iteration parity: read by thread 0 after the barrier */
+	__shared__ AccT s_wexc[S][WARPS];                             /* sums of the warps below, per ring slot */
+
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	const u32 lane_off = ((u32) (warp * VPT) * 32u + lane) * EPV;
+
+	/* prologue: ticket of sequence 0 in shared memory, ticket of sequence 1 in flight */
+	u32 tk = 0;
+	if (tid == 0) { s_tile[0] = atomicAdd(ticket, 1u); tk = atomicAdd(ticket, 1u); }
+	__syncthreads();
+	unsigned waited = 0;
+	for (u32 it = 0;; ++it) {
+		const int r = (int) it - AHEAD_;                    /* sequence number reduced now */
+		const int q = r - LAG_;                              /* sequence number scanned now */
+		/* all of these were written before the barrier of the previous iteration */
+		const u32 t_load = s_tile[it % NT];
+		const u32 t_red = r >= 0 ? s_tile[r % NT] : 0xffffffffu;
+		const u32 t_scan = q >= 0 ? s_tile[q % NT] : 0xffffffffu;
+		if (q >= 0 && t_scan >= num_tiles) break;            /* tickets are monotonic: nothing left */
+		if (tid == 0) { s_tile[(it + 1) % NT] = tk; tk = atomicAdd(ticket, 1u); }
+		/* the prefix word of the tile scanned below: requested now, looked at after the barrier */
+		AccT pfx = AccT(0);
+		bool pfx_ok = false;
+		if (lane == 0 && q >= 0) pfx_ok = spp_read<AccT>(pref + (size_t) t_scan * AW::N, epoch, pfx);
+
+		/* (1) start the copy of the new tile (own bytes only); always commit a group */
+		if (t_load < num_tiles) {
+			const size_t base = (size_t) t_load * TILE;
+			ElemT* dst = ring + (size_t) (it % S) * TILE;
+			if (base + TILE <= n) {
+#pragma unroll
+				for (int j = 0; j < VPT; ++j) {
+					const u32 o = lane_off + (u32) j * 32 * EPV;
+					spp_cp_async16(dst + o, in + base + o);
+				}
+			} else {
+#pragma unroll
+				for (int j = 0; j < VPT; ++j)
+#pragma unroll
+					for (int c = 0; c < EPV; ++c) {
+						const u32 o = lane_off + (u32) j * 32 * EPV + c;
+						dst[o] = (base + o < n) ? in[base + o] : ElemT(0);
+					}
+			}
+		}
+		spp_cp_async_commit();
+
+		/* (2) reduce the tile that has landed */
+		const bool red = r >= 0 && t_red < num_tiles;
+		if (red) {
+			spp_cp_async_wait<AHEAD_>();
+			const ElemT* src = ring + (size_t) (r % S) * TILE;
+			IntraT part[VPT];
+#pragma unroll
+			for (int j = 0; j < VPT; ++j) {
+				ElemT e[EPV];
+				*reinterpret_cast<uint4*>(e) = *reinterpret_cast<const uint4*>(src + lane_off + (u32) j * 32 * EPV);
+				IntraT s2 = IntraT(0);
+#pragma unroll
+				for (int c = 0; c < EPV; ++c) s2 += to_acc<ElemT, SumT, IntraT>(e[c]);
+				part[j] = s2;
+			}
+			IntraT sum = part[0];
+#pragma unroll
+			for (int j = 1; j < VPT; ++j) sum += part[j];
+			sum = warp_reduce_sum<IntraT>(sum);
+			if (lane == 0) s_wsum[it & 1][warp] = static_cast<AccT>(sum);
+		}
+		__syncthreads();                                     /* the only barrier of the iteration */
+		if (red && tid == 0) {
+			AccT total = AccT(0);
+#pragma unroll
+			for (int w = 0; w < WARPS; ++w) { s_wexc[r % S][w] = total; total += s_wsum[it & 1][w]; }
+			spp_publish<AccT>(agg + (size_t) t_red * AW::N, epoch, total);
+		}
+
+		/* (3) scan + store the tile whose prefix was requested above */
+		if (q >= 0) {
+			if (lane == 0) {
+				unsigned spins = 0;
+				while (!pfx_ok) {
+					if (++spins > (1u << 24)) { atomicExch(err_flag, 1); break; }
+					pfx_ok = spp_read<AccT>(pref + (size_t) t_scan * AW::N, epoch, pfx);
+				}
+				waited += spins;
+			}
+			/* lane 0 holds the tile's prefix; the sums of the warps below were prefix-summed by
+			 * thread 0 when the tile was reduced */
+			AccT warp_off = __shfl_sync(0xffffffffu, pfx, 0) + s_wexc[q % S][warp];
+			const ElemT* src = ring + (size_t) (q % S) * TILE;
+			const size_t base = (size_t) t_scan * TILE;
+			const bool full = base + TILE <= n;
+			AccT row_off = warp_off;
+#pragma unroll
+			for (int j = 0; j < VPT; ++j) {
+				const u32 o = lane_off + (u32) j * 32 * EPV;
+				ElemT e[EPV];
+				*reinterpret_cast<uint4*>(e) = *reinterpret_cast<const uint4*>(src + o);
+				IntraT v[EPV];
+#pragma unroll
+				for (int c = 0; c < EPV; ++c) v[c] = to_acc<ElemT, SumT, IntraT>(e[c]);
+#pragma unroll
+				for (int c = 1; c < EPV; ++c) v[c] += v[c - 1];
+				const IntraT incl = warp_inclusive_scan<IntraT>(v[EPV - 1], lane);
+				IntraT excl = __shfl_up_sync(0xffffffffu, incl, 1);
+				if (lane == 0) excl = IntraT(0);
+				const IntraT row_total = __shfl_sync(0xffffffffu, incl, 31);
+				const AccT b = row_off + static_cast<AccT>(excl);
+				row_off += static_cast<AccT>(row_total);
+				SumT ov[EPV];
+				if (std::is_same<SumT, float>::value) {
+					const IntraT bf = static_cast<IntraT>(b);
+					ov[0] = static_cast<SumT>(bf);
+#pragma unroll
+					for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(bf + v[c - 1]);
+				} else {
+					ov[0] = static_cast<SumT>(b);
+#pragma unroll
+					for (int c = 1; c < EPV; ++c) ov[c] = static_cast<SumT>(b + static_cast<AccT>(v[c - 1]));
+				}
+				const size_t idx = base + o;
+				if (full || idx + EPV <= n) {
+#pragma unroll
+					for (int c0 = 0; c0 < EPV; c0 += OCH) {
+						SumT chunk[OCH];
+#pragma unroll
+						for (int c = 0; c < OCH; ++c) chunk[c] = ov[c0 + c];
+						store_vec_cs<SumT, OCH>(out + idx + c0, chunk);
+					}
+				} else {
+#pragma unroll
+					for (int c = 0; c < EPV; ++c) if (idx + c < n) out[idx + c] = ov[c];
+				}
+			}
+		}
+	}
+	spp_cp_async_wait<0>();
+	if (waited) atomicAdd(reinterpret_cast<unsigned*>(err_flag) + 2, waited);   /* statistics: prefix polls */
+}
+
 #endif

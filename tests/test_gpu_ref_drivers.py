@@ -81,3 +81,43 @@ def test_reference_rng_bench_unchanged_maxint_and_bits():
     seeds = oracle.rng_seeds_dev_gid("xorshift64", 1, 5, G)
     want, _ = oracle.rng_generate("xorshift64", seeds, G, runs, bits=8)
     assert np.array_equal(got, want.reshape(-1))
+
+
+def _run_in(cwd, exe, *args):
+    path = os.path.join(REF, exe)
+    if not os.path.exists(path):
+        pytest.skip("%s not built (needs /root/reference at build time)" % exe)
+    r = subprocess.run([path] + list(args), capture_output=True, timeout=600, cwd=cwd)
+    assert r.returncode == 0, r.stdout[-1500:].decode(errors="replace") + r.stderr[-1500:].decode(errors="replace")
+    return r.stdout
+
+
+def test_reference_rng_bench_output_formats(tmp_path):
+    """The wire / on-disk formats either side of the RNG path (clo_rng_bench.c:204-274, 314-323;
+    read back by scripts/clo_rng_plot.py:33-57 and by dieharder): the unchanged driver writes
+    file-tsv (one run per line, tab separated, np.loadtxt-able), file-dh (dieharder header
+    "type: d / count / numbit", one number per line) and stdout-bin (raw little-endian uint32),
+    and all three carry the oracle's stream."""
+    import numpy as np
+    import oracle
+    rng, G, runs, seed, hash_ = "xorshift128", 512, 4, 9, "KNUTH(x)"
+    seeds = oracle.rng_seeds_dev_gid(rng, oracle.HASH_IDS[hash_], seed, G)
+    want, _ = oracle.rng_generate(rng, seeds, G, runs)
+    want = np.asarray(want).reshape(runs, G)
+    common = ["-r", rng, "-g", str(G), "-n", str(runs), "-s", str(seed), "--gid-hash", hash_, "-b", "32"]
+    # file-tsv: out_<rng>_gid_<hash>.tsv in the working directory
+    _run_in(str(tmp_path), "clo_rng_bench", "-o", "file-tsv", *common)
+    tsv = tmp_path / ("out_%s_gid_%s.tsv" % (rng, hash_))
+    assert tsv.exists()
+    img = np.loadtxt(str(tsv), dtype=np.uint32)                  # what clo_rng_plot.py does
+    assert img.shape == (runs, G) and np.array_equal(img, want)
+    assert tsv.read_text().splitlines()[0].count("\t") == G       # "%u\t" per value, "\n" per run
+    # file-dh: dieharder ASCII input
+    _run_in(str(tmp_path), "clo_rng_bench", "-o", "file-dh", *common)
+    dh = (tmp_path / ("out_%s_gid_%s.dh.txt" % (rng, hash_))).read_text().splitlines()
+    assert dh[0] == "type: d" and dh[1] == "count: %d" % (G * runs) and dh[2] == "numbit: 32"
+    assert np.array_equal(np.array([int(x) for x in dh[3:]], dtype=np.uint64).astype(np.uint32), want.reshape(-1))
+    # stdout-bin: raw words
+    raw = _run_in(str(tmp_path), "clo_rng_bench", "-o", "stdout-bin", *common)
+    assert len(raw) == 4 * G * runs
+    assert np.array_equal(np.frombuffer(raw, dtype="<u4"), want.reshape(-1))
