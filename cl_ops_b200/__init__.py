@@ -141,6 +141,15 @@ def lib():
         sig("clo_rng_get_size", sz, vp)
         sig("clo_rng_generate", vp, vp, vp, vp, sz, u32, u32, errp)
         sig("clo_rng_generate_host", u32, vp, vp, vp, sz, u32, u32, errp)
+        sig("clo_dist_new", vp, vp, vp, errp)
+        sig("clo_dist_destroy", None, vp)
+        sig("clo_dist_sort_setup", u32, vp, i, sz, u32, errp)
+        sig("clo_dist_sort_with_device_data", u32, vp, vp, vp, vp, sz, u64, vp, vp, sz, ctypes.POINTER(sz), errp)
+        sig("clo_dist_scan_with_device_data", vp, vp, vp, vp, vp, vp, sz, errp)
+        sig("clo_dist_rng_partition", None, u64, u32, u32, ctypes.POINTER(u64), ctypes.POINTER(u64))
+        sig("clo_dist_set_timing", None, vp, u32)
+        sig("clo_dist_get_phases", u32, vp, ctypes.POINTER(ctypes.c_float), u32)
+        sig("clo_dist_get_counts", u32, vp, ctypes.POINTER(u64), ctypes.POINTER(u64))
         _lib = L
     return _lib
 
@@ -529,3 +538,124 @@ def launch_count():
 
 def version():
     return lib().clo_b200_version().decode()
+
+
+# --------------------------------------------------------------------------
+# CloDist: the multi-GPU entry points (include/cl_ops/clo_b200.h, csrc/dist.cu)
+# --------------------------------------------------------------------------
+
+_AG_DEV = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+_BAR_DEV = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p)
+_AG_HOST = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
+class _DistComm(ctypes.Structure):
+    _fields_ = [("user", ctypes.c_void_p), ("rank", ctypes.c_uint32), ("world", ctypes.c_uint32),
+                ("all_gather_dev", _AG_DEV), ("barrier_dev", _BAR_DEV), ("all_gather_host", _AG_HOST)]
+
+
+class _RawDev:
+    """device memory at a raw address as a torch tensor (zero copy)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class CloDist:
+    """clo_dist_*: sample sort / scan / RNG partition over the GPUs of one box, one process per
+    GPU.  The three collectives the library asks for are served by torch.distributed (NCCL) on
+    torch's CURRENT stream, so `queue` must wrap that stream (Queue(ctx, stream=...))."""
+
+    def __init__(self, ctx, group=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist, self.group, self.ctx = torch, dist, group, ctx
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self._views = {}
+        self._flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+        def view(ptr, nbytes):
+            key = (ptr, nbytes)
+            t = self._views.get(key)
+            if t is None:
+                t = torch.as_tensor(_RawDev(ptr, nbytes), device=torch.device("cuda", torch.cuda.current_device()))
+                self._views[key] = t
+            return t
+
+        def ag_dev(user, send, recv, nbytes, stream):
+            try:
+                dist.all_gather_into_tensor(view(recv, nbytes * self.world), view(send, nbytes), group=group)
+                return 0
+            except Exception:          # the C side turns this into a GError
+                return 1
+
+        def bar_dev(user, stream):
+            try:
+                dist.all_reduce(self._flag, group=group)
+                return 0
+            except Exception:
+                return 1
+
+        def ag_host(user, send, recv, nbytes):
+            try:
+                mine = ctypes.string_at(send, nbytes)
+                parts = [None] * self.world
+                dist.all_gather_object(parts, mine, group=group)
+                ctypes.memmove(recv, b"".join(parts), nbytes * self.world)
+                return 0
+            except Exception:
+                return 1
+
+        self._cbs = (_AG_DEV(ag_dev), _BAR_DEV(bar_dev), _AG_HOST(ag_host))      # keep the thunks alive
+        self._comm = _DistComm(None, self.rank, self.world, *self._cbs)
+        e = _Err()
+        self.h = lib().clo_dist_new(ctx.h, ctypes.byref(self._comm), e.ref())
+        e.check()
+
+    def sort_setup(self, key_type, capacity, with_payload=False):
+        e = _Err()
+        lib().clo_dist_sort_setup(self.h, key_type, capacity, 1 if with_payload else 0, e.ref())
+        e.check()
+
+    def sort(self, queue, keys_in, payload_in, numel, keys_out, payload_out, out_capacity, gidx0=None):
+        """clo_dist_sort_with_device_data on Buffers; returns the number of elements received."""
+        n_out = ctypes.c_size_t(0)
+        e = _Err()
+        lib().clo_dist_sort_with_device_data(self.h, queue.h, keys_in.h, payload_in.h if payload_in else None, numel,
+                                             0xFFFFFFFFFFFFFFFF if gidx0 is None else gidx0, keys_out.h,
+                                             payload_out.h if payload_out else None, out_capacity, ctypes.byref(n_out), e.ref())
+        e.check()
+        return n_out.value
+
+    def scan(self, scanner, queue, buf_in, buf_out, numel):
+        e = _Err()
+        lib().clo_dist_scan_with_device_data(self.h, scanner.h, queue.h, buf_in.h, buf_out.h, numel, e.ref())
+        e.check()
+
+    @staticmethod
+    def rng_partition(total_streams, rank, world):
+        first, count = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        lib().clo_dist_rng_partition(total_streams, rank, world, ctypes.byref(first), ctypes.byref(count))
+        return first.value, count.value
+
+    def set_timing(self, on):
+        lib().clo_dist_set_timing(self.h, 1 if on else 0)
+
+    PHASES = ("samples+allgather", "splitters", "count", "sizes all-gather", "scatter to peers",
+              "barrier+sizes to host", "local sort")
+
+    def phases_ms(self):
+        out = (ctypes.c_float * 8)()
+        n = lib().clo_dist_get_phases(self.h, out, 8)
+        return {self.PHASES[k]: float(out[k]) for k in range(n)}
+
+    def counts(self):
+        s, r = (ctypes.c_uint64 * 16)(), (ctypes.c_uint64 * 16)()
+        lib().clo_dist_get_counts(self.h, s, r)
+        return list(s)[:self.world], list(r)[:self.world]
+
+    def destroy(self):
+        if self.h:
+            lib().clo_dist_destroy(self.h)
+            self.h = None
+            self._views = {}

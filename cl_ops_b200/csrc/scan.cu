@@ -278,6 +278,8 @@ struct ScanState {
 	size_t pp_tiles_cap = 0;
 	u32 pp_epoch = 0;
 	int use_pp = 1;            /* CLO_SCAN_KERNEL=classic selects the one-tile-per-CTA kernel */
+	int tma_flags = 0;         /* CLO_SCAN_TMA_FLAGS: 1 windowed propagator, 2 chain with 64-tile chunks, 4 no poll back-off */
+	int use_tma = 1;           /* CLO_SCAN_KERNEL=tma: the copy-engine kernel for same-size types (scan_tma.cuh) */
 };
 
 const size_t HDR_BYTES = 256;
@@ -375,6 +377,93 @@ cudaError_t launch_scan_pp(ScanState& st, const void* in, void* out, size_t n, c
 	return cudaGetLastError();
 }
 
+#include "scan_tma.cuh"
+
+typedef CUresult (*StmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static StmEncodeFn stm_encode_fn() {
+	static StmEncodeFn fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult qr;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+				qr == cudaDriverEntryPointSuccess) fn = (StmEncodeFn) p;
+	}
+	return fn;
+}
+
+/* a buffer of `bytes` bytes (a multiple of 128) as [bytes / 128] rows of 32 words; box = one tile */
+static bool stm_make_map(CUtensorMap* tm, const void* ptr, size_t bytes, int box_rows) {
+	StmEncodeFn enc = stm_encode_fn();
+	if (!enc) return false;
+	const cuuint64_t dims[2] = { 32, (cuuint64_t) (bytes / 128) };
+	const cuuint64_t strides[1] = { 128 };
+	const cuuint32_t box[2] = { 32, (cuuint32_t) box_rows };
+	const cuuint32_t estr[2] = { 1, 1 };
+	return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+		CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+		CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename ElemT, typename SumT>
+bool scan_tma_applicable(const ScanState& st, const void* in, const void* out, size_t n) {
+	return st.use_pp && st.use_tma && sizeof(ElemT) == sizeof(SumT) && n >= SPP_MIN_ELEMS &&
+		(n * sizeof(ElemT)) % 128 == 0 && (n * sizeof(ElemT)) / 128 < 0x7fffffffull &&
+		(reinterpret_cast<uintptr_t>(in) % 16) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0 && stm_encode_fn() != nullptr;
+}
+
+template <typename ElemT, typename SumT, int THREADS = 256, int AHEAD = 1, int LAG = 4, int SLACK = 0>
+cudaError_t launch_scan_tma(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) {
+	typedef typename AccOf<SumT>::type AccT;
+	typedef typename std::conditional<std::is_same<SumT, float>::value, float, AccT>::type IntraT;
+	typedef StmShape<THREADS, AHEAD, LAG, SLACK> Shape;
+	constexpr size_t TILE = (size_t) Shape::TILE_BYTES / sizeof(ElemT);
+	constexpr size_t SMEM = 1024 + (size_t) Shape::S * Shape::TILE_BYTES + (size_t) Shape::S * THREADS * sizeof(IntraT);
+	const size_t tiles = (n + TILE - 1) / TILE;
+	cudaError_t e;
+	CUtensorMap tm_in, tm_out;
+	if (!stm_make_map(&tm_in, in, n * sizeof(ElemT), Shape::ROWS) || !stm_make_map(&tm_out, out, n * sizeof(SumT), Shape::ROWS))
+		return cudaErrorInvalidValue;
+	if (tiles > st.pp_tiles_cap) {
+		size_t cap = tiles + tiles / 4 + 1024;
+		if ((e = st.pp.reserve(HDR_BYTES + cap * 4 * sizeof(u64))) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(st.pp.ptr, 0, st.pp.size, stream)) != cudaSuccess) return e;
+		st.pp_tiles_cap = cap; st.pp_epoch = 0;
+	}
+	if (st.pp_epoch >= 0xfffffff0u) {
+		if ((e = cudaMemsetAsync(st.pp.ptr, 0, st.pp.size, stream)) != cudaSuccess) return e;
+		st.pp_epoch = 0;
+	}
+	st.pp_epoch += 1;
+	u32* ticket = (u32*) st.pp.ptr;
+	int* err_flag = (int*) st.pp.ptr + 1;
+	u64* agg = (u64*) ((char*) st.pp.ptr + HDR_BYTES);
+	u64* pref = agg + st.pp_tiles_cap * 2;
+	if ((e = cudaMemsetAsync(ticket, 0, sizeof(u32), stream)) != cudaSuccess) return e;
+	auto kern = clo_scan_tma<ElemT, SumT, THREADS, AHEAD, LAG, SLACK>;
+	static bool configured[64] = {};
+	static int ctas_per_sm_dev[64] = {};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64) dev = 0;
+	if (!configured[dev]) {
+		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
+		int k = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&k, kern, THREADS, SMEM) != cudaSuccess || k < 1) k = 1;
+		ctas_per_sm_dev[dev] = k;
+		configured[dev] = true;
+	}
+	size_t workers = (size_t) sms * ctas_per_sm_dev[dev] - 1;
+	if (workers > tiles) workers = tiles;
+	kern<<<(unsigned) (1 + workers), THREADS, SMEM, stream>>>(tm_in, tm_out, (u32) tiles,
+		agg, pref, ticket, st.pp_epoch, (const SumT*) carry, err_flag, st.tma_flags);
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
+}
+
 template <typename ElemT, typename SumT>
 bool scan_pp_applicable(const ScanState& st, const void* in, const void* out, size_t n) {
 	constexpr int EPV = sizeof(ElemT) >= 8 ? 2 : 4;
@@ -389,19 +478,33 @@ cudaError_t launch_scan<E, S>(ScanState& st, const void* in, void* out, size_t n
 	if (scan_pp_applicable<E, S>(st, in, out, n)) return launch_scan_pp<E, S>(st, in, out, n, carry, sms, stream); \
 	return launch_scan_cfg<E, S, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream); \
 }
+/* same-size pairs: the copy-engine kernel first (scan_tma.cuh), then the cp.async ring */
+#define CLO_SCAN_TMA_PAIR(E, S) \
+template <> \
+cudaError_t launch_scan<E, S>(ScanState& st, const void* in, void* out, size_t n, const void* carry, int sms, cudaStream_t stream) { \
+	if (scan_tma_applicable<E, S>(st, in, out, n)) return launch_scan_tma<E, S>(st, in, out, n, carry, sms, stream); \
+	if (scan_pp_applicable<E, S>(st, in, out, n)) return launch_scan_pp<E, S>(st, in, out, n, carry, sms, stream); \
+	return launch_scan_cfg<E, S, SCAN_THREADS, SCAN_VPT, SCAN_MIN_CTAS>(st, in, out, n, carry, stream); \
+}
 CLO_SCAN_PP_PAIR(unsigned int, unsigned long long)
-CLO_SCAN_PP_PAIR(int, int)
+CLO_SCAN_TMA_PAIR(int, int)
 CLO_SCAN_PP_PAIR(int, long long)
 
 CLO_SCAN_PP_PAIR(float, double)
-CLO_SCAN_PP_PAIR(unsigned long long, unsigned long long)
-CLO_SCAN_PP_PAIR(double, double)
+CLO_SCAN_TMA_PAIR(unsigned long long, unsigned long long)
+CLO_SCAN_TMA_PAIR(long long, long long)
+CLO_SCAN_TMA_PAIR(double, double)
 #undef CLO_SCAN_PP_PAIR
+#undef CLO_SCAN_TMA_PAIR
 
 /* tuning variants of the headline type pair */
 template <>
 cudaError_t launch_scan<unsigned int, unsigned int>(ScanState& st, const void* in, void* out, size_t n,
 		const void* carry, int sms, cudaStream_t stream) {
+	if (scan_tma_applicable<unsigned int, unsigned int>(st, in, out, n)) {
+		if (st.cfg == 32) return launch_scan_tma<unsigned int, unsigned int, 256, 1, 3, 1>(st, in, out, n, carry, sms, stream);
+		return launch_scan_tma<unsigned int, unsigned int>(st, in, out, n, carry, sms, stream);
+	}
 	if (scan_pp_applicable<unsigned int, unsigned int>(st, in, out, n)) {
 		switch (st.cfg) {      /* CLO_SCAN_CFG 10..: shapes of the persistent kernel */
 		case 11: return launch_scan_pp<unsigned int, unsigned int, 512, 2, 1, 4>(st, in, out, n, carry, sms, stream);
@@ -429,6 +532,10 @@ cudaError_t launch_scan<unsigned int, unsigned int>(ScanState& st, const void* i
 template <>
 cudaError_t launch_scan<float, float>(ScanState& st, const void* in, void* out, size_t n,
 		const void* carry, int sms, cudaStream_t stream) {
+	if (scan_tma_applicable<float, float>(st, in, out, n)) {
+		if (st.cfg == 32) return launch_scan_tma<float, float, 256, 1, 3, 1>(st, in, out, n, carry, sms, stream);
+		return launch_scan_tma<float, float>(st, in, out, n, carry, sms, stream);
+	}
 	if (scan_pp_applicable<float, float>(st, in, out, n)) {
 		switch (st.cfg) {      /* CLO_SCAN_CFG 10..: shapes of the persistent kernel */
 		case 11: return launch_scan_pp<float, float, 512, 2, 1, 4>(st, in, out, n, carry, sms, stream);
@@ -598,20 +705,29 @@ static CCLEvent* blelloch_scan_with_device_data(CloScan* scanner, CCLQueue* cq_e
 	return scan_device(scanner, cq_exec, data_in, data_out, NULL, numel, err);
 }
 
-static const char* const kScanKernels[] = { "clo_scan_pp", "clo_scan_lookback", "clo_scan_reduce_partial", "clo_scan_reduce_final" };
+static const char* const kScanKernels[] = { "clo_scan_tma", "clo_scan_pp", "clo_scan_lookback", "clo_scan_reduce_partial", "clo_scan_reduce_final" };
 
-static cl_uint blelloch_get_num_kernels(CloScan* scanner, GError** err) { (void) scanner; (void) err; return 4; }
+static cl_uint blelloch_get_num_kernels(CloScan* scanner, GError** err) { (void) scanner; (void) err; return 5; }
 
 static const char* blelloch_get_kernel_name(CloScan* scanner, cl_uint i, GError** err) {
 	(void) scanner;
-	if (i >= 4) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
+	if (i >= 5) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return NULL; }
 	return kScanKernels[i];
 }
 
 static size_t blelloch_get_localmem_usage(CloScan* scanner, cl_uint i, size_t lws_max, size_t numel, GError** err) {
 	(void) lws_max; (void) numel;
-	if (i >= 4) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
+	if (i >= 5) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "kernel index %u out of range", i); return 0; }
 	const size_t acc = clo_type_sizeof(scanner->sum_type) == 8 || scanner->sum_type >= CLO_FLOAT ? 8 : 4;
+	if (i == 0) {
+		/* clo_scan_tma: ring of AHEAD + LAG + 1 slots of 256 x 64 bytes (+ 1 KB alignment), the lanes-
+		 * below sums per slot, mbarriers, tickets, warp totals */
+		typedef StmShape<256, 1, 4, 0> Shape;
+		const size_t intra = scanner->sum_type == CLO_FLOAT ? 4 : acc;
+		return 1024 + (size_t) Shape::S * Shape::TILE_BYTES + (size_t) Shape::S * 256 * intra +
+			Shape::S * 8 + (Shape::S + 2) * 4 + (2 + Shape::S) * 8 * acc;
+	}
+	i -= 1;
 	if (i == 0) {
 		/* clo_scan_pp: ring of AHEAD + 1 + LAG tiles of 256 threads x 4 vectors of 16 bytes, the
 		 * per-slot warp totals and the ticket ring */
@@ -651,7 +767,9 @@ extern "C" CloScan* clo_scan_new(const char* type, const char* options, CCLConte
 	s->data = NULL;
 	s->fn = fn; s->rfn = find_reduce((int) elem_type, (int) sum_type);
 	{ const char* c = getenv("CLO_SCAN_CFG"); s->st.cfg = (c && *c) ? atoi(c) : 0; }
-	{ const char* c = getenv("CLO_SCAN_KERNEL"); s->st.use_pp = (c && strcmp(c, "classic") == 0) ? 0 : 1; }
+	{ const char* c = getenv("CLO_SCAN_KERNEL"); s->st.use_pp = (c && strcmp(c, "classic") == 0) ? 0 : 1;
+	  s->st.use_tma = (c && (strcmp(c, "pp") == 0 || strcmp(c, "classic") == 0)) ? 0 : 1;
+	  const char* f = getenv("CLO_SCAN_TMA_FLAGS"); s->st.tma_flags = (f && *f) ? atoi(f) : 0; }
 	GError* ierr = NULL;
 	s->impl_def.init(s, options, &ierr);
 	if (ierr) { g_propagate_error(err, ierr); clo_scan_destroy(s); return NULL; }

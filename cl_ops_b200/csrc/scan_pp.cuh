@@ -146,6 +146,75 @@ __device__ __forceinline__ void spp_propagate(u64* __restrict__ agg, u64* __rest
 	}
 }
 
+/* ---- propagator, second form: a CHAIN OF WARPS.
+ * The windowed propagator above pays, per window, an L2 round trip for the loads it can only
+ * issue after the previous window's length is known, three CTA barriers and a shared-memory
+ * scan; an AGG word waits up to a whole window period before anybody looks at it.  Measured with
+ * the copy-engine workers (scan_tma.cuh), whose tiles come 1.5 us apart: hundreds of prefix polls
+ * per tile, and the polls themselves slow the propagator down further.
+ * Here warp w owns the chunks w, w + WARPS, ... of 32 * PU consecutive tiles.  Its lanes poll
+ * their own AGG words back to back (no barrier, no other warp involved), one warp scan turns
+ * them into exclusive sums, and the chunk's base comes from the previous chunk's warp through a
+ * shared-memory mailbox -- the only serial link, a few dozen cycles instead of an L2 round
+ * trip.  A tile's PREF leaves about one poll period after the last AGG of its chunk arrived. */
+template <typename AccT, int THREADS, int PU>
+__device__ __forceinline__ void spp_propagate_chain(u64* __restrict__ agg, u64* __restrict__ pref, u32 num_tiles,
+		u32 epoch, AccT carry, int* __restrict__ err_flag) {
+	typedef AccWords<AccT> AW;
+	constexpr int WARPS = THREADS / 32;
+	constexpr u32 CH = 32 * PU;
+	__shared__ AccT s_box[WARPS];
+	__shared__ u32 s_seq[WARPS];
+	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+	if (tid < WARPS) s_seq[tid] = 0;
+	__syncthreads();
+	if (tid == 0) { s_box[0] = carry; __threadfence_block(); *reinterpret_cast<volatile u32*>(&s_seq[0]) = 1u; }
+	const u32 num_chunks = (num_tiles + CH - 1) / CH;
+	for (u32 c = (u32) warp; c < num_chunks; c += WARPS) {
+		const u32 t0 = c * CH + (u32) lane * PU;
+		AccT v[PU];
+		bool ok[PU];
+#pragma unroll
+		for (int u = 0; u < PU; ++u) { v[u] = AccT(0); ok[u] = t0 + u >= num_tiles; }
+		unsigned spins = 0;
+		for (;;) {
+#pragma unroll
+			for (int u = 0; u < PU; ++u)
+				if (!ok[u]) ok[u] = spp_read<AccT>(agg + (size_t) (t0 + u) * AW::N, epoch, v[u]);
+			bool all = true;
+#pragma unroll
+			for (int u = 0; u < PU; ++u) all = all && ok[u];
+			if (__all_sync(0xffffffffu, all)) break;
+			if (++spins > (1u << 22)) { if (lane == 0) atomicExch(err_flag, 1); break; }
+		}
+		AccT inc[PU];
+		inc[0] = v[0];
+#pragma unroll
+		for (int u = 1; u < PU; ++u) inc[u] = inc[u - 1] + v[u];
+		const AccT wincl = warp_inclusive_scan<AccT>(inc[PU - 1], lane);
+		const AccT total = __shfl_sync(0xffffffffu, wincl, 31);
+		AccT base = AccT(0);
+		if (lane == 0) {
+			unsigned w2 = 0;
+			while (*reinterpret_cast<volatile u32*>(&s_seq[warp]) != c + 1u) {
+				if (++w2 > (1u << 26)) { atomicExch(err_flag, 1); break; }
+			}
+			__threadfence_block();
+			base = *reinterpret_cast<volatile AccT*>(&s_box[warp]);
+			const int nw = warp + 1 == WARPS ? 0 : warp + 1;
+			*reinterpret_cast<volatile AccT*>(&s_box[nw]) = base + total;
+			__threadfence_block();
+			*reinterpret_cast<volatile u32*>(&s_seq[nw]) = c + 2u;
+		}
+		base = __shfl_sync(0xffffffffu, base, 0);
+		const AccT lane_excl = base + (wincl - inc[PU - 1]);
+#pragma unroll
+		for (int u = 0; u < PU; ++u)
+			if (t0 + u < num_tiles)
+				spp_publish<AccT>(pref + (size_t) (t0 + u) * AW::N, epoch, u == 0 ? lane_excl : lane_excl + inc[u - 1]);
+	}
+}
+
 /* ---- the kernel: block 0 propagates, the others work */
 template <typename ElemT, typename SumT, int THREADS, int VPT_ = SPP_VPT, int AHEAD_ = SPP_AHEAD, int LAG_ = SPP_LAG>
 __global__ void __launch_bounds__(THREADS, 2)
@@ -168,7 +237,7 @@ clo_scan_pp(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u32 
 
 	const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
 	if (blockIdx.x == 0) {
-		spp_propagate<AccT, THREADS>(agg, pref, num_tiles, epoch, carry, err_flag);
+		spp_propagate_chain<AccT, THREADS, 1>(agg, pref, num_tiles, epoch, carry, err_flag);
 		return;
 	}
 
@@ -343,7 +412,7 @@ clo_scan_pp1b(const ElemT* __restrict__ in, SumT* __restrict__ out, size_t n, u3
 
 	const AccT carry = carry_in ? to_acc<SumT, SumT, AccT>(*carry_in) : AccT(0);
 	if (blockIdx.x == 0) {
-		spp_propagate<AccT, THREADS>(agg, pref, num_tiles, epoch, carry, err_flag);
+		spp_propagate_chain<AccT, THREADS, 1>(agg, pref, num_tiles, epoch, carry, err_flag);
 		return;
 	}
 

@@ -85,10 +85,27 @@ class GpuOps:
         return keys, payload
 
     # ---- fused partition + exchange over peer memory (one process per GPU, one box)
-    def setup_peer_exchange(self, capacity, key_dtype, with_payload, group=None):
+    def setup_peer_exchange(self, capacity, key_dtype, with_payload, group=None, impl=None):
         """Allocate this rank's receive buffers (capacity elements), export them with CUDA IPC
         and map every peer's: afterwards the partition's scatter kernel writes each bucket
-        straight into its destination rank over NVLink.  Collective; call once."""
+        straight into its destination rank over NVLink.  Collective; call once.
+
+        impl "c" (default; CLO_DIST_IMPL overrides): the whole sort is ONE C-ABI call,
+        clo_dist_sort_with_device_data (csrc/dist.cu) -- samples, splitters, sizes, scatter,
+        barrier and local sort are orchestrated by the library, torch.distributed only serves
+        its three collective callbacks.  impl "py": the same steps driven from this module
+        (what the gloo tests exercise on the CPU)."""
+        impl = impl or os.environ.get("CLO_DIST_IMPL", "c")
+        if impl == "c":
+            self.cd = self.clo.CloDist(self.ctx, group)
+            self.cd.sort_setup(self.key_type, capacity, with_payload)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.cd_with_payload = with_payload
+            self.cd_capacity = capacity
+            self.cd_out_k = torch.empty(max(1, capacity), dtype=key_dtype, device=dev)
+            self.cd_out_p = torch.empty(max(1, capacity), dtype=torch.int32, device=dev) if with_payload else None
+            self.cd_bufs = (self._buf(self.cd_out_k), self._buf(self.cd_out_p) if with_payload else None)
+            return
         P, r = dist.get_world_size(group), dist.get_rank(group)
         kb = torch.empty(0, dtype=key_dtype).element_size()
         own = [self.clo.Buffer(self.ctx, size=max(1, capacity) * kb)]
@@ -153,7 +170,38 @@ class GpuOps:
             bi.destroy(); bo.destroy()
         return out, None
 
+    def sort_c(self, keys, payload, gidx0, profile):
+        """the C-ABI sample sort; returns (keys, payload, info) like sample_sort, or None when a
+        receive buffer is too small (the library then moved nothing)"""
+        cd = self.cd
+        cd.set_timing(bool(profile))
+        bk = self._buf(keys)
+        bp = self._buf(payload) if payload is not None else None
+        try:
+            n_out = cd.sort(self.queue, bk, bp, keys.numel(), self.cd_bufs[0], self.cd_bufs[1], self.cd_capacity, gidx0)
+        except self.clo.CloError as e:
+            if "receive" in e.message:
+                return None
+            raise
+        finally:
+            bk.destroy()
+            if bp is not None:
+                bp.destroy()
+        sent, recv = cd.counts()
+        r = dist.get_rank(cd.group)
+        info = {"sent": keys.numel() - sent[r], "received": n_out, "gidx0": gidx0, "fused": True, "impl": "c",
+                "send_counts": sent, "recv_counts": recv, "phases_ms": cd.phases_ms() if profile else {}}
+        out_p = self.cd_out_p[:n_out] if payload is not None else None
+        return self.cd_out_k[:n_out], out_p, info
+
     def close(self):
+        if getattr(self, "cd", None) is not None:
+            for b in self.cd_bufs:
+                if b is not None:
+                    b.destroy()
+            self.cd.destroy()
+            self.cd = None
+            self.cd_out_k = self.cd_out_p = None
         if self.peer:
             dist.barrier(group=self.peer["group"])
             for i, bl in enumerate(self.peer["maps"]):
@@ -289,6 +337,13 @@ def sample_sort(keys, payload, ops, key_bits, group=None, samples_per_rank=None,
     if P == 1:
         k, p = ops.sort(keys, payload)
         return k, p, {"sent": 0, "received": n_local, "gidx0": 0}
+
+    # the product path on GPUs: one call into the library (clo_dist_sort_with_device_data)
+    if getattr(ops, "cd", None) is not None and ops.cd_with_payload == (payload is not None):
+        res = ops.sort_c(keys, payload, gidx0, profile)
+        if res is not None:
+            return res
+        # a receive buffer would overflow (nothing was written): the NCCL all-to-all-v path below
 
     # 1) regular samples of the unsorted local data.  One all-gather carries, per rank:
     #    [n_local, s, sample keys (cap), sample positions (cap)]; global indices are formed

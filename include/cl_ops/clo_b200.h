@@ -92,6 +92,69 @@ cl_bool clo_sort_b200_debug(CloSort* sorter, CCLQueue* cq, cl_ulong out[18]);
 void clo_sort_b200_set_timing(CloSort* sorter, cl_bool on);
 cl_uint clo_sort_b200_get_timing(CloSort* sorter, float* out_ms, cl_uint cap);
 
+/* ---- multi-GPU: one process (or thread) per GPU of one box --------------------------
+ * The reference is single-device (clo_sort_abstract.c:335 takes "the first device in the
+ * context"); these entry points shard its three operators over the GPUs of a box.  The
+ * library moves the DATA itself (kernels that write straight into peer memory over
+ * NVLink / NVSwitch, mapped with CUDA IPC); the caller supplies three tiny collectives
+ * for the bookkeeping -- with NCCL each one is a single call (INTEGRATION.md has the code). */
+typedef struct clo_dist CloDist;
+typedef struct clo_dist_comm {
+	void* user;
+	cl_uint rank, world;                 /* world <= 16 */
+	/* device all-gather ordered on `cuda_stream`: every rank gives `bytes` bytes at send_dev and
+	 * gets world * bytes at recv_dev, in rank order (ncclAllGather).  Return 0 on success. */
+	int (*all_gather_dev)(void* user, const void* send_dev, void* recv_dev, size_t bytes, void* cuda_stream);
+	/* device barrier ordered on `cuda_stream`: what follows it on the stream runs after everything
+	 * the other ranks enqueued before their call has completed (a 4-byte ncclAllReduce will do) */
+	int (*barrier_dev)(void* user, void* cuda_stream);
+	/* host all-gather, used by clo_dist_sort_setup only (the 64-byte IPC handles) */
+	int (*all_gather_host)(void* user, const void* send, void* recv, size_t bytes);
+} CloDistComm;
+
+#define CLO_DIST_GIDX_AUTO (~(cl_ulong) 0)
+
+CloDist* clo_dist_new(CCLContext* ctx, const CloDistComm* comm, GError** err);
+void clo_dist_destroy(CloDist* d);   /* collective when clo_dist_sort_setup was called */
+
+/* Collective.  Allocates this rank's receive buffers (`capacity` elements of key_type, 4 or 8
+ * bytes wide, plus cl_uint payloads when with_payload), exchanges their IPC handles and maps
+ * every peer's.  capacity must cover the largest slice a rank can receive (the splitters keep
+ * slices within a few per cent of numel for any key distribution: 1.25 * numel is ample). */
+cl_bool clo_dist_sort_setup(CloDist* d, CloType key_type, size_t capacity, cl_bool with_payload, GError** err);
+
+/* Collective.  Globally stable sort (raw key bits ascending, satradix semantics) of the
+ * concatenation of every rank's keys_in[0..numel) in rank order.  Sample sort: regular samples
+ * -> all-gather -> world-1 splitters (key, global index), chosen on the device by this
+ * library's rank kernel -> clo_partition_count -> all-gather of the bucket sizes ->
+ * clo_partition_scatter writes every bucket into the receive buffer of its destination rank
+ * -> barrier -> local LSD radix sort into keys_out (and payload_out).  This rank ends up with
+ * *numel_out elements: the rank-th slice of the sorted sequence.  gidx0 = global index of this
+ * rank's first element, or CLO_DIST_GIDX_AUTO (derived from the gathered counts).  Blocks the
+ * host once (the received size).  Fails, writing nothing, when a slice exceeds the capacity
+ * given to clo_dist_sort_setup or out_capacity. */
+cl_bool clo_dist_sort_with_device_data(CloDist* d, CCLQueue* cq_exec, CCLBuffer* keys_in, CCLBuffer* payload_in,
+	size_t numel, cl_ulong gidx0, CCLBuffer* keys_out, CCLBuffer* payload_out, size_t out_capacity,
+	size_t* numel_out, GError** err);
+
+/* Collective.  Exclusive scan of the concatenation of every rank's data_in (rank order):
+ * per-GPU total -> all-gather of `world` totals -> local scan with the carry-in kept in device
+ * memory.  Integer results are bit-exact (wrap-around kept); float carries are summed in f64. */
+CCLEvent* clo_dist_scan_with_device_data(CloDist* d, CloScan* scanner, CCLQueue* cq_exec, CCLBuffer* data_in,
+	CCLBuffer* data_out, size_t numel, GError** err);
+
+/* RNG streams partition without communication: rank r owns the contiguous work-items
+ * [*first, *first + *count) of total_streams; pass them to clo_rng_new_dev_gid_offset. */
+void clo_dist_rng_partition(cl_ulong total_streams, cl_uint rank, cl_uint world, cl_ulong* first, cl_ulong* count);
+
+/* Device time of the phases of the last clo_dist_sort call (CUDA events on the queue's stream):
+ * samples + all-gather, splitters, count, sizes all-gather + slots, scatter, barrier, local sort.
+ * Timing is off until clo_dist_set_timing(d, CL_TRUE).  Returns the number of values written. */
+void clo_dist_set_timing(CloDist* d, cl_bool on);
+cl_uint clo_dist_get_phases(CloDist* d, float* out_ms, cl_uint cap);
+/* what the last sort sent to / received from every rank (world values each) */
+cl_bool clo_dist_get_counts(CloDist* d, cl_ulong* sent, cl_ulong* received);
+
 /* Library / device info. */
 const char* clo_b200_version(void);
 /* number of this library's kernels launched since load (bench evidence) */

@@ -326,6 +326,25 @@ def test_sample_sort_two_gpus_fused_exchange():
     assert "DIST GPU OK" in r.stdout
 
 
+def test_c_client_dist_sort():
+    """tools/dist_sort_nccl.c: a plain C program (one forked process per GPU, NCCL for the three
+    callbacks) sorts and scans over the GPUs of the box through clo_dist_* and checks itself --
+    the multi-GPU layer is reachable without Python.  With one GPU the world is 1."""
+    import json
+    import os
+    import subprocess
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "dist_sort_nccl")
+    if not os.path.exists(exe):
+        pytest.skip("tools/dist_sort_nccl not built (needs nccl.h at build time)")
+    gpus = min(2, torch.cuda.device_count())
+    r = subprocess.run([exe, str(gpus), "22"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["ok"] is True and line["gpus"] == gpus
+
+
 @pytest.mark.parametrize("et,with_payload", [(oracle.UINT, False), (oracle.ULONG, False), (oracle.UINT, True), (oracle.ULONG, True)])
 def test_satradix_wide_lookback_words(clo, ctx, queue, et, with_payload, monkeypatch):
     """n >= 2^31 switches the tile-prefix words to 64 bits; CLO_RADIX_WIDE=1 forces that path at
