@@ -148,13 +148,31 @@ extern "C" __global__ void clo_jit_gselect(const CLO_SORT_ELEM_TYPE* in, CLO_SOR
 	}
 	out[rank] = mine;
 }
+
+/* satradix with an arbitrary get_key: the key of every element, as raw bits zero-extended to a
+ * 32- or 64-bit word (clo_sort_satradix.cl:58-61 takes bit b of `CLO_SORT_KEY_GET(value)`), next
+ * to the element's index */
+extern "C" __global__ void clo_jit_extract_keys(const CLO_SORT_ELEM_TYPE* in, void* keys, unsigned int* idx, unsigned long long n) {
+	const unsigned long long i = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const CLO_SORT_ELEM_TYPE x = in[i];
+	const CLO_SORT_KEY_TYPE k = (CLO_SORT_KEY_TYPE) (CLO_SORT_KEY_GET(x));
+	unsigned long long raw;
+	if (sizeof(k) == 1) raw = *reinterpret_cast<const unsigned char*>(&k);
+	else if (sizeof(k) == 2) raw = *reinterpret_cast<const unsigned short*>(&k);
+	else if (sizeof(k) == 4) raw = *reinterpret_cast<const unsigned int*>(&k);
+	else raw = *reinterpret_cast<const unsigned long long*>(&k);
+	if (sizeof(k) <= 4) reinterpret_cast<unsigned int*>(keys)[i] = (unsigned int) raw;
+	else reinterpret_cast<unsigned long long*>(keys)[i] = raw;
+	idx[i] = (unsigned int) i;
+}
 )SRC";
 
 } // namespace
 
 struct CloJitSort {
 	CUmodule mod = nullptr;
-	CUfunction f_step = nullptr, f_pad = nullptr, f_gselect = nullptr;
+	CUfunction f_step = nullptr, f_pad = nullptr, f_gselect = nullptr, f_extract = nullptr;
 	std::string source;
 	CloScratch pad;
 };
@@ -200,7 +218,8 @@ CloJitSort* clo_jit_sort_new(CloType elem_type, CloType key_type, const char* co
 	if (drv.ModuleLoadData(&j->mod, cubin.data()) != 0 ||
 			drv.ModuleGetFunction(&j->f_step, j->mod, "clo_jit_bitonic_step") != 0 ||
 			drv.ModuleGetFunction(&j->f_pad, j->mod, "clo_jit_init_pad") != 0 ||
-			drv.ModuleGetFunction(&j->f_gselect, j->mod, "clo_jit_gselect") != 0) {
+			drv.ModuleGetFunction(&j->f_gselect, j->mod, "clo_jit_gselect") != 0 ||
+			drv.ModuleGetFunction(&j->f_extract, j->mod, "clo_jit_extract_keys") != 0) {
 		msg = "loading the run-time compiled sort module failed";
 		if (j->mod) drv.ModuleUnload(j->mod);
 		delete j;
@@ -259,6 +278,54 @@ cudaError_t clo_jit_gselect_sort(CloJitSort* j, const void* in, void* out, size_
 	if (driver().LaunchKernel(j->f_gselect, (unsigned) ((n + 255) / 256), 1, 1, 256, 1, 1, 0, stream, args, nullptr) != 0) return cudaErrorLaunchFailure;
 	CLO_COUNT_LAUNCH(1);
 	return cudaSuccess;
+}
+
+/* satradix for a get_key string outside the menu: extract (key, index) with the run-time compiled
+ * kernel, sort the pairs by the key's raw bits with the library's own stable LSD passes, gather
+ * the elements.  Same result as the reference's passes over CLO_SORT_KEY_GET(value): a stable
+ * sort by raw key bits, ascending. */
+namespace {
+template <typename T>
+__global__ void clo_radix_gather(const T* __restrict__ in, const unsigned int* __restrict__ idx, T* __restrict__ out, size_t n) {
+	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = in[idx[i]];
+}
+}
+
+cudaError_t clo_jit_radix_sort(CloJitSort* j, CloRadixState* rs, int sm_count, size_t elem_size, size_t key_size,
+		uint32_t sorted_bits, const void* in, void* out, size_t n, cudaStream_t stream, const char** err_msg) {
+	if (n == 0) return cudaSuccess;
+	if (n > 0xffffffffull) { if (err_msg) *err_msg = "satradix with a run-time compiled get_key sorts at most 2^32 elements"; return cudaErrorInvalidValue; }
+	const size_t kw = key_size <= 4 ? 4 : 8;
+	const size_t keys_bytes = (n * kw + 255) & ~(size_t) 255, idx_bytes = (n * 4 + 255) & ~(size_t) 255;
+	const bool in_place = in == out;
+	cudaError_t e;
+	if ((e = j->pad.reserve(keys_bytes + idx_bytes + (in_place ? n * elem_size : 0))) != cudaSuccess) return e;
+	void* keys = j->pad.ptr;
+	unsigned int* idx = (unsigned int*) ((char*) j->pad.ptr + keys_bytes);
+	const void* src = in;
+	if (in_place) {
+		void* copy = (char*) j->pad.ptr + keys_bytes + idx_bytes;
+		if ((e = cudaMemcpyAsync(copy, in, n * elem_size, cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
+		src = copy;
+	}
+	unsigned long long nn = n;
+	void* args[] = { (void*) &src, &keys, &idx, &nn };
+	if (driver().LaunchKernel(j->f_extract, (unsigned) ((n + 255) / 256), 1, 1, 256, 1, 1, 0, stream, args, nullptr) != 0) return cudaErrorLaunchFailure;
+	CLO_COUNT_LAUNCH(1);
+	CloKeySpec ks = {};
+	ks.mask = ~0ull; ks.shift = 0; ks.elem_bits = ks.key_bits = (uint32_t) (8 * kw);
+	ks.elem_signed = 0; ks.key_kind = CLO_KIND_UNSIGNED; ks.descending = 0; ks.identity = 1;
+	if ((e = clo_radix_sort(rs, sm_count, kw, ks, sorted_bits < 8 * key_size ? sorted_bits : (uint32_t) (8 * key_size), keys, keys, idx, idx, n, stream, err_msg)) != cudaSuccess) return e;
+	const unsigned grid = (unsigned) ((n + 255) / 256);
+	switch (elem_size) {
+	case 1: clo_radix_gather<unsigned char><<<grid, 256, 0, stream>>>((const unsigned char*) src, idx, (unsigned char*) out, n); break;
+	case 2: clo_radix_gather<unsigned short><<<grid, 256, 0, stream>>>((const unsigned short*) src, idx, (unsigned short*) out, n); break;
+	case 4: clo_radix_gather<unsigned int><<<grid, 256, 0, stream>>>((const unsigned int*) src, idx, (unsigned int*) out, n); break;
+	default: clo_radix_gather<unsigned long long><<<grid, 256, 0, stream>>>((const unsigned long long*) src, idx, (unsigned long long*) out, n); break;
+	}
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
 }
 
 /* =====================================================================================

@@ -193,9 +193,12 @@ static CCLEvent* satradix_sort_with_device_data(CloSort* sorter, CCLQueue* cq_ex
 	ccl_event* evt = clo_queue_begin(cq_exec, "clo_radix_onesweep");
 	const char* msg = NULL;
 	void* dst = data_out ? data_out->ptr : data_in->ptr;
-	cudaError_t rc = clo_radix_sort(sorter->rs, clo_sm_count(cq_exec->ctx->dev.ordinal),
-		clo_type_sizeof(sorter->elem_type), sorter->ks, bits, data_in->ptr, dst, NULL, NULL,
-		numel, cq_exec->stream, &msg);
+	cudaError_t rc = sorter->jit
+		? clo_jit_radix_sort(sorter->jit, sorter->rs, clo_sm_count(cq_exec->ctx->dev.ordinal),
+			clo_type_sizeof(sorter->elem_type), clo_type_sizeof(sorter->key_type), bits, data_in->ptr, dst, numel, cq_exec->stream, &msg)
+		: clo_radix_sort(sorter->rs, clo_sm_count(cq_exec->ctx->dev.ordinal),
+			clo_type_sizeof(sorter->elem_type), sorter->ks, bits, data_in->ptr, dst, NULL, NULL,
+			numel, cq_exec->stream, &msg);
 	clo_queue_end(cq_exec, evt);
 	if (rc != cudaSuccess && msg) {
 		g_set_error(err, CLO_ERROR, rc == cudaErrorLaunchFailure ? CLO_ERROR_LIBRARY : CLO_ERROR_ARGS, "%s", msg);
@@ -431,8 +434,11 @@ extern "C" CloSort* clo_sort_new(const char* type, const char* options, CCLConte
 	 * taken in the shared-memory tile (maxsfs) -- clo_sort_abitonic.c:486-542 */
 	if (!ierr && def == &clo_sort_abitonic_def)
 		clo_bitonic_set_fusion(s->bs, (int) s->maxps, s->maxsfs > 13u ? 13 : (int) s->maxsfs);
-	const bool in_menu = parse_get_key(get_key, shift, mask) && parse_compare(compare, desc);
 	const bool comparison_sort = def != &clo_sort_satradix_def;
+	/* satradix never looks at `compare` (the reference defines the macro and its radix kernels
+	 * do not use it): raw key bits ascending whatever it says */
+	const bool in_menu = parse_get_key(get_key, shift, mask) && (parse_compare(compare, desc) || !comparison_sort);
+	if (!comparison_sort) desc = 0;
 	if (!ierr && !in_menu && comparison_sort) {
 		/* the reference compiles ANY macro body into its kernels (clo_sort_abstract.c:144-168);
 		 * strings outside the precompiled menu are compiled here too, with NVRTC */
@@ -443,12 +449,14 @@ extern "C" CloSort* clo_sort_new(const char* type, const char* options, CCLConte
 		shift = 0; mask = ~0ull; desc = 0;
 	}
 	if (!ierr && !in_menu && !comparison_sort) {
-		if (!parse_get_key(get_key, shift, mask))
-			g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
-				"get_key '%s' is not supported by satradix (menu: (x), ((x) >> K), ((x) & M), (((x) >> K) & M))", get_key);
-		else
-			g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS,
-				"compare '%s' is not supported by satradix (menu: ((a) > (b)), ((a) < (b)))", compare);
+		/* a get_key string outside the menu (clo_sort_abstract.c:157-168 accepts any macro body;
+		 * the digit is cut from it at clo_sort_satradix.cl:61): the key extraction is compiled at
+		 * run time, the passes are the library's own (jit.cu: clo_jit_radix_sort) */
+		std::string msg;
+		CloDeviceGuard g(ctx->dev.ordinal);
+		s->jit = clo_jit_sort_new(et, kt, NULL, get_key, msg);
+		if (!s->jit) g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg.c_str());
+		shift = 0; mask = ~0ull; desc = 0;
 	}
 	if (!ierr && !s->jit && kind_of(et) == CLO_KIND_FLOAT && (shift != 0 || mask != ~0ull || kt != et))
 		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_ARGS, "a floating-point element only supports the identity key");

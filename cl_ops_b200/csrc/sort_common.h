@@ -125,6 +125,9 @@ void clo_jit_sort_free(CloJitSort* j);
 const char* clo_jit_sort_source(CloJitSort* j);
 cudaError_t clo_jit_bitonic_sort(CloJitSort* j, size_t elem_size, void* data, size_t n, cudaStream_t stream);
 cudaError_t clo_jit_gselect_sort(CloJitSort* j, const void* in, void* out, size_t n, cudaStream_t stream);
+/* satradix with a run-time compiled get_key: (key, index) extraction, pair sort, gather */
+cudaError_t clo_jit_radix_sort(CloJitSort* j, CloRadixState* rs, int sm_count, size_t elem_size, size_t key_size,
+	uint32_t sorted_bits, const void* in, void* out, size_t n, cudaStream_t stream, const char** err_msg);
 #endif
 
 #endif

@@ -216,11 +216,14 @@ def test_sort_errors(clo, ctx):
         with pytest.raises(clo.CloError) as ei:
             clo.CloSort("abitonic", ctx, oracle.UINT, **kw)
         assert ei.value.code == clo.CLO_ERROR_ARGS
+    # the radix kernels never expand CLO_SORT_COMPARE (clo_sort_satradix.cl defines no comparison):
+    # any compare string is accepted and ignored; a get_key that does not compile is an error
+    clo.CloSort("satradix", ctx, oracle.UINT, compare="((a) >= (b))").destroy()
     with pytest.raises(clo.CloError) as ei:
-        clo.CloSort("satradix", ctx, oracle.UINT, compare="((a) >= (b))")
+        clo.CloSort("satradix", ctx, oracle.UINT, get_key="((x) >>> 3)")
     assert ei.value.code == clo.CLO_ERROR_ARGS
     s = clo.CloSort("satradix", ctx, oracle.UINT)
-    assert s.kernel_names() == ["clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep"]
+    assert s.kernel_names() == ["clo_radix_histogram", "clo_radix_scan_bins", "clo_radix_onesweep_v6"]
     s.destroy()
 
 
@@ -442,10 +445,40 @@ def test_custom_macro_strings_gselect_and_errors(clo, ctx, queue):
     with pytest.raises(clo.CloError) as ei:
         clo.CloSort("sbitonic", ctx, oracle.UINT, compare="((a) >>> (b))")
     assert ei.value.code == clo.CLO_ERROR_ARGS and "do not compile" in str(ei.value)
-    # the radix sort has no comparator to splice: still the menu only
-    with pytest.raises(clo.CloError) as ei:
-        clo.CloSort("satradix", ctx, oracle.UINT, get_key="((x) * 3)")
-    assert ei.value.code == clo.CLO_ERROR_ARGS
+
+
+@pytest.mark.parametrize("et,kt,get_key,keyfn", [
+    (oracle.UINT, oracle.UINT, "((x) * 40503u)", lambda x: (x.astype(np.uint64) * 40503 % (1 << 32)).astype(np.uint64)),
+    (oracle.ULONG, oracle.USHORT, "(((x) >> 7) ^ (x))", lambda x: ((x >> np.uint64(7)) ^ x) & np.uint64(0xFFFF)),
+    (oracle.INT, oracle.CHAR, "((x) / 3)", lambda x: (np.trunc(x.astype(np.int64) / 3).astype(np.int64).astype(np.int8)).view(np.uint8).astype(np.uint64)),
+    (oracle.USHORT, oracle.UINT, "(~(x))", lambda x: (~x.astype(np.uint32)).astype(np.uint64) & np.uint64(0xFFFF)),
+])
+@pytest.mark.parametrize("n", [1, 777, (1 << 18) + 11])
+def test_satradix_custom_get_key_is_compiled_at_run_time(clo, ctx, queue, et, kt, get_key, keyfn, n):
+    """satradix with a get_key string outside the menu (clo_sort_abstract.c:157-168 splices any macro
+    body; clo_sort_satradix.cl:58-61 cuts the digit from `CLO_SORT_KEY_GET(value)`): the key
+    extraction is built with NVRTC and the result is the stable sort by the key's raw bits -- the
+    low elem-size bits of them, as the reference's host loop only walks those
+    (clo_sort_satradix.c:166-169).  In place and out of place."""
+    import torch
+    rng = np.random.default_rng(n + et)
+    a = _rand(rng, et, n)
+    k = keyfn(a)
+    eb = 8 * a.dtype.itemsize
+    if eb < 64:
+        k = k & np.uint64((1 << eb) - 1)
+    want = a[np.argsort(k, kind="stable")]
+    s = clo.CloSort("satradix", ctx, et, key_type=kt, get_key=get_key)
+    got = s.with_host_data(a, queue)
+    assert np.array_equal(got, want)
+    sdt = {1: np.int8, 2: np.int16, 4: np.int32, 8: np.int64}[a.dtype.itemsize]
+    t = torch.from_numpy(a.view(sdt).copy()).cuda()
+    b = clo.Buffer.wrap_tensor(ctx, t)
+    s.with_device_data(queue, b, None, n)          # in place
+    queue.finish()
+    assert np.array_equal(t.cpu().numpy().view(a.dtype), want)
+    b.destroy()
+    s.destroy()
 
 
 def test_introspection_getters_name_real_kernels(clo, ctx):
