@@ -1,14 +1,15 @@
 """oracle/build_ref_drivers.py -- compile the reference's OWN benchmark drivers, unchanged, from
 where they lie under /root/reference (src/benchmarks/clo_sort_bench.c, clo_scan_bench.c,
-clo_bench.c; the error macros of src/cl_ops/common/_g_err_macros.h) against this repository's
+clo_rng_bench.c, clo_bench.c, src/tests/test_rng.c; the error macros of
+src/cl_ops/common/_g_err_macros.h) against this repository's
 headers (include/, include/compat/{glib,cf4ocl2}.h) and link them with cl_ops_b200/libcl_ops.so.
 
 Outputs go to oracle/_ref/ only (git-ignored binaries; no reference source is copied).  This is
 the "existing src/benchmarks drivers relink unchanged" check of BASELINE.json's north_star:
 the drivers verify their own results (sorted order, clo_sort_bench.c:216-226; scan == serial
 host scan, clo_scan_bench.c:253-270), so running them on the GPU box is a parity test written
-by the reference's author.  Not built: clo_rng_bench / test_rng (they compile an OpenCL kernel
-string through ccl_program_*, which has no CUDA meaning without NVRTC).
+by the reference's author.  clo_rng_bench and test_rng compile an OpenCL C kernel string through
+ccl_program_*: the library's NVRTC-backed program / kernel shim (csrc/jit.cu) builds it at run time.
 """
 import os
 import subprocess
