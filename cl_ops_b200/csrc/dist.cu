@@ -47,6 +47,7 @@ __global__ void clo_dist_sample(const void* __restrict__ keys, u64 numel, u32 ca
 __global__ void clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 cap, u32 rank, u64 gidx0_given,
 		int kb, void* __restrict__ spl_keys, u64* __restrict__ spl_idx, u64* __restrict__ info) {
 	__shared__ u64 s_keys[256];
+	__shared__ unsigned char s_valid[256];
 	__shared__ u64 s_g0[DIST_MAX_WORLD + 1];
 	__shared__ u32 s_cnt[DIST_MAX_WORLD + 1];
 	const u32 row_w = 2 + cap;
@@ -69,16 +70,14 @@ __global__ void clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 c
 		const bool v = o < slots && j < (u32) all[(size_t) r * row_w + 1];
 		__syncthreads();
 		s_keys[threadIdx.x] = v ? all[(size_t) r * row_w + 2 + j] : ~0ull;
-		/* an empty slot must never count: give it the largest key AND let the position decide */
+		s_valid[threadIdx.x] = v ? 1 : 0;            /* an empty slot never counts */
 		__syncthreads();
 		if (valid) {
 			const u32 lim = min(256u, slots - base);
+#pragma unroll 8
 			for (u32 t = 0; t < lim; ++t) {
-				const u32 pos = base + t;
-				const u32 pr = pos / cap, pj = pos % cap;
-				const bool pv = pj < (u32) all[(size_t) pr * row_w + 1];
 				const u64 k = s_keys[t];
-				below += (pv && (k < my_key || (k == my_key && pos < me))) ? 1u : 0u;
+				below += (s_valid[t] && (k < my_key || (k == my_key && base + t < me))) ? 1u : 0u;
 			}
 		}
 	}

@@ -39,22 +39,11 @@ const int MAX_PASSES = 8;
 #ifndef CLO_IPT_U32
 #define CLO_IPT_U32 16
 #endif
-const int LB_FIRST = 4;     /* look-back window: first load batch */
-const int LB_NEXT = 4;      /* ... and the following ones */
 
 struct PassCfg {
 	int passes;
 	u32 start_bit[MAX_PASSES];
 	u32 dmask[MAX_PASSES];
-};
-
-/* look-back word: 2 flag bits on top of the value */
-template <typename LbT> struct Lb;
-template <> struct Lb<u32> {
-	static constexpr u32 AGG = 1u << 30, PREFIX = 2u << 30, VAL = (1u << 30) - 1, FLAGS = 3u << 30;
-};
-template <> struct Lb<u64> {
-	static constexpr u64 AGG = 1ull << 62, PREFIX = 2ull << 62, VAL = (1ull << 62) - 1, FLAGS = 3ull << 62;
 };
 
 /* raw element -> (promoted) key bits the digits are cut from */
@@ -158,15 +147,6 @@ clo_radix_scan_bins(const u64* __restrict__ ghist, u64* __restrict__ bins_base) 
 
 /* -------------------------------------------------------------- onesweep */
 
-/* A digit functor for the sample-sort partition: bucket = number of splitters
- * (key, global index) that are <= (my key, my global index). */
-struct SplitterArgs {
-	const void* keys;       /* nparts-1 splitter keys, element type */
-	const u64* idx;         /* nparts-1 splitter global indices */
-	u32 count;              /* nparts-1 */
-	u64 gidx0;              /* global index of element 0 */
-};
-
 /* How a key gets its rank among the equal-digit keys of its warp:
  *  RANK_BALLOT  digit-match masks from 8 ballots + a leader's read-modify-write of
  *               the warp's shared histogram.  ~45 ALU-pipe instructions per 32 keys:
@@ -183,321 +163,9 @@ struct SplitterArgs {
  *               depends on the atomic order; only speed does. */
 enum { RANK_BALLOT = 0, RANK_ATOMIC = 1 };
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY, bool PARTITION, typename LbT,
-	int THREADS, int IPT, int RANK_MODE, int LBF = LB_FIRST, int LBN = LB_NEXT>
-__global__ void __launch_bounds__(THREADS, (THREADS >= 384 ? 2 : 4))
-clo_radix_onesweep(const ElemT* __restrict__ in, ElemT* __restrict__ out,
-		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n,
-		LbT* __restrict__ lookback, u32* __restrict__ ticket, const u64* __restrict__ bins_base,
-		u32 start_bit, u32 dmask, CloKeySpec ks, SplitterArgs sp, int* __restrict__ err_flag, int prof_on) {
-	constexpr int WARPS = THREADS / 32;
-	constexpr int TILE = THREADS * IPT;
-	constexpr bool VERIFY = (RANK_MODE == RANK_ATOMIC);
-	/* the (digit, index) word is needed whenever the key alone cannot prove stability or
-	 * give the digit back: payloads, extracted keys, the splitter partition */
-	constexpr bool USE_INFO = HAS_VAL || !IDENTITY || PARTITION;
-	static_assert(THREADS >= RADIX, "one thread per digit is needed");
-	static_assert(TILE <= 65536, "index-in-tile must fit 16 bits");
-
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	u32* whist = reinterpret_cast<u32*>(smem_raw);                         /* [WARPS][RADIX] */
-	u32* s_dstart = whist + WARPS * RADIX;                                 /* [RADIX] */
-	LbT* s_goff = reinterpret_cast<LbT*>(s_dstart + RADIX);                /* [RADIX] (u64-sized slot) */
-	u32* s_misc = s_dstart + RADIX + 2 * RADIX;                            /* [16]: tile, warp sums, flags */
-	ElemT* skeys = reinterpret_cast<ElemT*>(s_misc + 16);                  /* [TILE] */
-	u32* sinfo = reinterpret_cast<u32*>(skeys + TILE);                     /* [TILE] digit<<16 | index, if USE_INFO */
-	u32* svals = sinfo + TILE;                                             /* [TILE] if HAS_VAL (then USE_INFO) */
-
-	const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-	/* bits of this digit and below (keys-only verification) */
-	const ElemT low_mask = (ElemT) ((((ElemT) dmask) << start_bit) | ((((ElemT) 1) << start_bit) - 1));
-
-	/* optional phase profile (CLO_RADIX_PROFILE=1): thread 0 accumulates cycles per phase
-	 * into the u64 counters behind the status words */
-	long long t_prev = 0;
-	u64* prof = reinterpret_cast<u64*>(err_flag + 16);
-	auto mark = [&](int phase) {
-		if (prof_on && tid == 0) {
-			const long long t = clock64();
-			atomicAdd(prof + phase, (u64) (t - t_prev));
-			t_prev = t;
-		}
-	};
-	if (prof_on && tid == 0) t_prev = clock64();
-
-	if (tid == 0) s_misc[0] = atomicAdd(ticket, 1u);
-	for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
-	__syncthreads();
-	mark(0);
-	const u32 tile = s_misc[0];
-	const size_t tile_base = (size_t) tile * TILE;
-	const bool full = tile_base + TILE <= n;
-	const u32 tile_count = full ? (u32) TILE : (u32) (n - tile_base);
-
-	/* The whole tile body is instantiated twice, for full tiles (no per-item bounds
-	 * checks at all) and for the single partial tile at the end. */
-	auto body = [&](auto full_tag) {
-		constexpr bool FULL = decltype(full_tag)::value;
-		/* ---- load, warp-striped: item i of lane l is element warp*32*IPT + i*32 + l */
-		ElemT key[IPT];
-		u32 val[HAS_VAL ? IPT : 1];
-		u32 pos2[(IPT + 1) / 2];   /* ranks, two 16-bit halves per register */
-#pragma unroll
-		for (int i = 0; i < (IPT + 1) / 2; ++i) pos2[i] = 0;
-		const u32 wbase = (u32) warp * 32u * IPT + lane;
-	#pragma unroll
-		for (int i = 0; i < IPT; ++i) {
-			const u32 local = wbase + i * 32u;
-			if (FULL || local < tile_count) {
-				key[i] = __ldcs(in + tile_base + local);
-				if (HAS_VAL) val[i] = __ldcs(vin + tile_base + local);
-			} else {
-				key[i] = ElemT(0);
-				if (HAS_VAL) val[i] = 0;
-			}
-		}
-
-		/* splitter table for the partition variant (tiny: <= 15 entries) */
-		ElemT sp_key[PARTITION ? 15 : 1];
-		u64 sp_idx[PARTITION ? 15 : 1];
-		if (PARTITION) {
-	#pragma unroll
-			for (int s = 0; s < 15; ++s) {
-				if (s < (int) sp.count) {
-					sp_key[s] = reinterpret_cast<const ElemT*>(sp.keys)[s];
-					sp_idx[s] = sp.idx[s];
-				} else { sp_key[s] = ElemT(0); sp_idx[s] = 0; }
-			}
-		}
-
-		auto digit_of = [&](ElemT k, u32 local) -> u32 {
-			if (PARTITION) {
-				const u64 g = sp.gidx0 + tile_base + local;
-				u32 b = 0;
-	#pragma unroll
-				for (int s = 0; s < 15; ++s)
-					if (s < (int) sp.count && (sp_key[s] < k || (sp_key[s] == k && sp_idx[s] <= g))) ++b;
-				return b;
-			}
-			return radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
-		};
-
-		u32* wh = whist + warp * RADIX;
-
-		/* ---- rank inside the warp: pos[i] = number of earlier keys of this warp with my digit;
-		 *      afterwards wh[d] = number of keys of this warp with digit d */
-		auto rank_ballot = [&]() {
-	#pragma unroll
-			for (int i = 0; i < IPT; ++i) {
-				const u32 local = wbase + i * 32u;
-				const bool valid = FULL || local < tile_count;
-				const u32 d = digit_of(key[i], local);
-				u32 peers = match_digit_ballot(d);
-				if (!FULL) peers &= __ballot_sync(0xffffffffu, valid);
-				const u32 lt = peers & lanemask_lt();
-				u32 old = 0;
-				if (valid && lt == 0) {            /* first lane of its digit group */
-					old = wh[d];
-					wh[d] = old + __popc(peers);
-				}
-				__syncwarp();
-				const int leader = __ffs(peers) - 1;
-				old = __shfl_sync(0xffffffffu, old, leader & 31);
-				pos2[i >> 1] |= (old + __popc(lt)) << (16 * (i & 1));
-			}
-		};
-		auto rank_atomic = [&]() {
-	#pragma unroll
-			for (int i = 0; i < IPT; ++i) {
-				const u32 local = wbase + i * 32u;
-				if (FULL || local < tile_count)
-					pos2[i >> 1] |= atomicAdd(&wh[digit_of(key[i], local)], 1u) << (16 * (i & 1));
-			}
-		};
-
-		/* ---- per digit (thread d): tile count = sum of the warps' counts (independent loads) */
-		auto digit_count = [&]() -> u32 {
-			u32 count = 0;
-			if (tid < RADIX) {
-#pragma unroll
-				for (int w = 0; w < WARPS; ++w) count += whist[w * RADIX + tid];
-			}
-			return count;
-		};
-		/* exclusive scan of the 256 counts -> start of each digit inside the tile; the per-warp
-		 * counts become dstart[d] + (count of d in lower warps), so staging needs one lookup.
-		 * Contains a barrier. */
-		auto digit_starts = [&](u32 count) {
-			const u32 incl = warp_inclusive_scan<u32>(count, lane);
-			if (tid < RADIX && lane == 31) s_misc[1 + warp] = incl;
-			__syncthreads();
-			if (tid < RADIX) {
-				u32 off = 0;
-#pragma unroll
-				for (int w = 0; w < RADIX / 32; ++w) if (w < warp) off += s_misc[1 + w];
-				const u32 ds = off + incl - count;
-				s_dstart[tid] = ds;
-				u32 c[WARPS];
-#pragma unroll
-				for (int w = 0; w < WARPS; ++w) c[w] = whist[w * RADIX + tid];
-				u32 run = ds;
-#pragma unroll
-				for (int w = 0; w < WARPS; ++w) { whist[w * RADIX + tid] = run; run += c[w]; }
-			}
-		};
-		/* ---- stage the tile in digit order.  VERIFY_KEYS (keys only, identity key): the keys
-		 *      themselves prove a correct pass, nothing else is staged.  Otherwise the
-		 *      (digit, index-in-tile) word is staged beside the key. */
-		auto stage = [&]() {
-#pragma unroll
-			for (int i = 0; i < IPT; ++i) {
-				const u32 local = wbase + i * 32u;
-				if (FULL || local < tile_count) {
-					const u32 d = digit_of(key[i], local);
-					const u32 p = wh[d] + ((pos2[i >> 1] >> (16 * (i & 1))) & 0xffffu);
-					skeys[p] = key[i];
-					if (USE_INFO) sinfo[p] = (d << 16) | local;
-					if (HAS_VAL) svals[p] = val[i];
-				}
-			}
-		};
-		/* ---- write out: element j of the staged tile -> goff[digit] + j.  Returns whether the
-		 *      staged order was seen to violate the pass invariant:
-		 *      with the info word: (digit, index-in-tile) strictly increasing == stable;
-		 *      keys only: the input of pass p is sorted on the bits below start_bit, so the
-		 *      output is correct iff (key & low_mask) is non-decreasing along the staged tile,
-		 *      low_mask covering this digit and everything below it. */
-		auto write_out = [&](bool verify) -> bool {
-			bool bad = false;
-#pragma unroll
-			for (int i = 0; i < IPT; ++i) {
-				const u32 j = (u32) tid + i * THREADS;
-				if (FULL || j < tile_count) {
-					const ElemT k = skeys[j];
-					u32 d;
-					if (USE_INFO) {
-						const u32 info = sinfo[j];
-						if (verify && j > 0 && info <= sinfo[j - 1]) bad = true;
-						d = info >> 16;
-					} else {
-						if (verify && j > 0 && (k & low_mask) < (skeys[j - 1] & low_mask)) bad = true;
-						d = radix_digit<ElemT, IDENTITY>(k, ks, start_bit, dmask);
-					}
-					const LbT o = s_goff[d] + (LbT) j;
-					out[o] = k;
-					if (HAS_VAL) vout[o] = svals[j];
-				}
-			}
-			return bad;
-		};
-
-		if (prof_on) { if (tid == 0 && key[IPT - 1] == ElemT(0x5a5a5a5a)) prof[15] = 1; mark(1); }  /* loads landed */
-		if (RANK_MODE == RANK_ATOMIC) rank_atomic(); else rank_ballot();
-		__syncthreads();
-		mark(2);
-
-		const u32 count = digit_count();
-		/* publish the tile aggregate as early as possible */
-		LbT* lb_mine = lookback + (size_t) tile * RADIX;
-		if (tid < RADIX) {
-			if (tile == 0) st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | (LbT) count));
-			else st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::AGG | (LbT) count));
-		}
-		digit_starts(count);
-		__syncthreads();
-		mark(3);
-
-		/* Staging needs tile-local offsets only.  The warps that own a digit (tid < RADIX)
-		 * resolve their look-back first -- so the tile's inclusive prefix is published as
-		 * early as possible, which keeps every successor's walk short -- while the other
-		 * warps already stage their keys. */
-		/* ---- decoupled look-back, one digit per thread */
-		auto look_back = [&]() {
-			LbT excl = 0;
-			if (tile > 0) {
-				long long p = (long long) tile - 1;
-				unsigned spins = 0;
-				bool done = false;
-				/* A window of predecessor words is loaded at once (all loads in flight
-				 * together) and consumed nearest first.  While tiles wait here, their
-				 * successors must walk over them, so a short window makes the backlog --
-				 * and with it every walk -- longer; after a first small window the walk
-				 * continues with wide ones. */
-				auto walk = [&](auto batch_tag) {
-					constexpr int B = decltype(batch_tag)::value;
-					LbT w[B];
-#pragma unroll
-					for (int k = 0; k < B; ++k)
-						w[k] = (p - k >= 0) ? ld_relaxed(lookback + (size_t) (p - k) * RADIX + tid) : (LbT) Lb<LbT>::PREFIX;
-#pragma unroll
-					for (int k = 0; k < B; ++k) {
-						if (!done) {
-							const LbT f = w[k] & Lb<LbT>::FLAGS;
-							if (f == 0) {            /* not published yet: retry from here */
-								if (++spins > SPIN_LIMIT) { atomicExch(err_flag, 1); done = true; }
-								break;
-							}
-							excl += w[k] & Lb<LbT>::VAL;
-							--p;
-							if (f == Lb<LbT>::PREFIX) done = true;
-						}
-					}
-				};
-				const long long lb_t0 = prof_on ? clock64() : 0;
-				u32 rounds = 1;
-				walk(std::integral_constant<int, LBF>{});
-				while (!done) { walk(std::integral_constant<int, LBN>{}); ++rounds; }
-				if (prof_on && tid == 0) {
-					atomicAdd(prof + 7, (u64) (clock64() - lb_t0));   /* cycles inside the walk */
-					atomicAdd(prof + 8, (u64) rounds);                  /* window loads */
-					atomicAdd(prof + 9, (u64) spins);                   /* unpublished words met */
-					atomicAdd(prof + 10, (u64) ((long long) tile - 1 - p));  /* predecessors consumed */
-				}
-				st_relaxed(lb_mine + tid, (LbT) (Lb<LbT>::PREFIX | ((excl + count) & Lb<LbT>::VAL)));
-			}
-			/* modular arithmetic in LbT: the final index goff[d] + j is < n */
-			s_goff[tid] = (LbT) bins_base[tid] + excl - (LbT) s_dstart[tid];
-		};
-		if (tid < RADIX) look_back();
-		stage();
-		mark(4);
-		__syncthreads();
-		mark(5);
-
-		const bool bad = write_out(VERIFY);
-		mark(6);
-
-		if (VERIFY) {
-			if (__syncthreads_or(bad ? 1 : 0)) {
-				/* The atomic ranks were not in lane order somewhere in this tile: redo the tile
-				 * with the ballot ranks.  Digit counts, hence every offset, are unchanged. */
-				if (tid == 0) atomicAdd(err_flag + 1, 1);
-				for (int i = tid; i < WARPS * RADIX; i += THREADS) whist[i] = 0;
-				__syncthreads();
-#pragma unroll
-				for (int i = 0; i < (IPT + 1) / 2; ++i) pos2[i] = 0;
-				/* keys (and payloads) are re-read: their registers were released after staging */
-#pragma unroll
-				for (int i = 0; i < IPT; ++i) {
-					const u32 local = wbase + i * 32u;
-					if (FULL || local < tile_count) {
-						key[i] = in[tile_base + local];
-						if (HAS_VAL) val[i] = vin[tile_base + local];
-					}
-				}
-				rank_ballot();
-				__syncthreads();
-				const u32 count2 = digit_count();
-				digit_starts(count2);
-				__syncthreads();
-				stage();
-				__syncthreads();
-				write_out(false);
-			}
-		}
-	};
-	if (full) body(std::true_type{}); else body(std::false_type{});
-}
+/* (the one-tile-per-CTA look-back kernel of round 1 and its splitter-as-digit partition variant
+ * were removed in round 2: every configuration runs a persistent kernel, radix_pp.cuh or
+ * radix_v6.cuh) */
 
 #include "radix_pp.cuh"
 
@@ -523,7 +191,6 @@ struct CloRadixState {
 	CloScratch aux_vals;
 	CloScratch work;         /* [err | ghist | bins_base | tickets | lookback...] */
 	CloScratch pp;           /* AGG + PREF words of the persistent kernel (self-cleaning) */
-	int kernel_pp = 1;       /* CLO_RADIX_KERNEL=classic selects the one-tile-per-CTA kernel */
 	int kernel_v6 = 1;       /* keys-only sorts use the two-barrier kernel; CLO_RADIX_KERNEL=pp|classic turn it off */
 	int force_wide = 0;      /* CLO_RADIX_WIDE=1: 64-bit look-back words whatever n is (test hook for the >= 2^31 path) */
 	int rank_atomic = 1;     /* CLO_RADIX_RANK=ballot selects the ballot ranks */
@@ -549,7 +216,6 @@ CloRadixState* clo_radix_state_new() {
 	const char* e = getenv("CLO_RADIX_RANK");
 	st->rank_atomic = (e && strcmp(e, "ballot") == 0) ? 0 : 1;
 	const char* kk = getenv("CLO_RADIX_KERNEL");
-	st->kernel_pp = (kk && strcmp(kk, "classic") == 0) ? 0 : 1;
 	st->kernel_v6 = (kk && (strcmp(kk, "classic") == 0 || strcmp(kk, "pp") == 0)) ? 0 : 1;
 	const char* ppf = getenv("CLO_RADIX_PP_FLAGS");
 	g_pp_flags = (ppf && *ppf) ? atoi(ppf) : 0;
@@ -637,28 +303,6 @@ cudaError_t prepare_work(CloRadixState* st, size_t tiles, int passes, size_t lb_
 	return cudaMemsetAsync(base, 0, L.zero_bytes, stream);
 }
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int RANK_MODE, int THREADS, int IPT, int LBF = LB_FIRST, int LBN = LB_NEXT>
-cudaError_t launch_onesweep(const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n,
-		LbT* lookback, u32* ticket, const u64* bins, u32 start_bit, u32 dmask, const CloKeySpec& ks,
-		int* err, cudaStream_t stream) {
-	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT, (HAS_VAL || !IDENTITY)>();
-	auto kern = clo_radix_onesweep<ElemT, HAS_VAL, IDENTITY, false, LbT, THREADS, IPT, RANK_MODE, LBF, LBN>;
-	static bool configured[64] = {};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	if (dev < 0 || dev >= 64 || !configured[dev]) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM);
-		if (e != cudaSuccess) return e;
-		if (dev >= 0 && dev < 64) configured[dev] = true;
-	}
-	const size_t tiles = (n + (size_t) THREADS * IPT - 1) / ((size_t) THREADS * IPT);
-	SplitterArgs sp = { nullptr, nullptr, 0, 0 };
-	kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, lookback, ticket, bins,
-		start_bit, dmask, ks, sp, err, g_radix_profile);
-	CLO_COUNT_LAUNCH(1);
-	return cudaGetLastError();
-}
-
 template <typename ElemT, bool HAS_VAL, bool IDENTITY, typename LbT, int RANK_MODE, int THREADS, int IPT>
 cudaError_t launch_onesweep_pp(const ElemT* in, ElemT* out, const u32* vin, u32* vout, size_t n,
 		LbT* agg, LbT* pref, u32* ticket, const u64* bins, u32 start_bit, u32 dmask, const CloKeySpec& ks,
@@ -714,7 +358,7 @@ cudaError_t launch_histogram(const ElemT* src, size_t n, u64* ghist, const PassC
 	}
 }
 
-template <typename ElemT, bool HAS_VAL, bool IDENTITY, int THREADS, int IPT, int LBF = LB_FIRST, int LBN = LB_NEXT>
+template <typename ElemT, bool HAS_VAL, bool IDENTITY, int THREADS, int IPT>
 cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks, u32 sorted_bits,
 		const ElemT* src, ElemT* dst, const u32* vsrc, u32* vdst, size_t n, cudaStream_t stream) {
 	constexpr size_t TILE = (size_t) THREADS * IPT;
@@ -728,13 +372,11 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		cfg.dmask[p] = (1u << (rem < (u32) RADIX_BITS ? rem : (u32) RADIX_BITS)) - 1;
 	}
 	const size_t tiles = (n + TILE - 1) / TILE;
-	const bool use_pp = st->kernel_pp != 0;
-	/* look-back words: the classic kernel keeps 30 value bits, the persistent ones 31 (every
-	 * prefix and offset is a count of keys, i.e. < n) */
-	const bool wide = st->force_wide || n >= (use_pp ? (1ull << 31) : (1ull << 30));
+	/* tile-prefix words keep 31 value bits (every prefix and offset is a count of keys, i.e. < n) */
+	const bool wide = st->force_wide || n >= (1ull << 31);
 	WorkLayout L;
-	if ((e = prepare_work(st, use_pp ? 0 : tiles, cfg.passes, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
-	if (use_pp) {
+	if ((e = prepare_work(st, 0, cfg.passes, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
+	{
 		/* AGG + PREF words, shared by all passes; zeroed when (re)allocated, self-cleaning after */
 		const size_t need = 2 * tiles * RADIX * (wide ? 8 : 4);
 		if (need > st->pp.size) {
@@ -778,7 +420,7 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		u32* ticket = L.tickets + p;
 		bool done_v6 = false;
 		if constexpr (IDENTITY && sizeof(ElemT) >= 4 && THREADS > RADIX) {
-			if (use_pp && st->kernel_v6) {
+			if (st->kernel_v6) {
 				char* agg = (char*) st->pp.ptr;
 				char* pref = agg + tiles * RADIX * (wide ? 8 : 4);
 				e = clo_radix_v6_pass((int) sizeof(ElemT), wide ? 1 : 0, THREADS * IPT, cur, nxt, HAS_VAL ? vcur : nullptr, HAS_VAL ? vnxt : nullptr, n, agg, pref, ticket,
@@ -787,7 +429,7 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 			}
 		}
 		if (done_v6) {
-		} else if (use_pp) {
+		} else {
 			const u64* bins = L.bins + p * RADIX;
 			if (wide) {
 				u64* agg = (u64*) st->pp.ptr; u64* pref = agg + tiles * RADIX;
@@ -800,12 +442,6 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 					? launch_onesweep_pp<ElemT, HAS_VAL, IDENTITY, u32, 1, THREADS, IPT>(cur, nxt, vcur, vnxt, n, agg, pref, ticket, bins, cfg.start_bit[p], cfg.dmask[p], ks, L.err, sm_count, stream)
 					: launch_onesweep_pp<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT>(cur, nxt, vcur, vnxt, n, agg, pref, ticket, bins, cfg.start_bit[p], cfg.dmask[p], ks, L.err, sm_count, stream);
 			}
-		} else if (wide) {
-			u64* lb = (u64*) L.lookback + (size_t) p * tiles * RADIX;
-			e = launch_onesweep<ElemT, HAS_VAL, IDENTITY, u64, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
-		} else {
-			u32* lb = (u32*) L.lookback + (size_t) p * tiles * RADIX;
-			e = launch_onesweep<ElemT, HAS_VAL, IDENTITY, u32, 0, THREADS, IPT, LBF, LBN>(cur, nxt, vcur, vnxt, n, lb, ticket, L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], ks, L.err, stream);
 		}
 		if (e != cudaSuccess) return e;
 		st->mark(stream);
@@ -884,96 +520,6 @@ cudaError_t clo_radix_sort(CloRadixState* st, int sm_count, size_t elem_size, co
 
 /* ------------------------------------------------------------- partition */
 
-namespace {
-
-template <typename ElemT, bool HAS_VAL>
-cudaError_t partition_typed(CloRadixState* st, const ElemT* in, const u32* vin, ElemT* out, u32* vout, size_t n,
-		u64 gidx0, const void* sk, const u64* si, u32 nparts, u64* counts_out, cudaStream_t stream);
-
-/* bucket histogram: counts per bucket (same bucket function as the onesweep variant) */
-template <typename ElemT, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-clo_partition_histogram(const ElemT* __restrict__ in, size_t n, SplitterArgs sp, u64* __restrict__ ghist) {
-	__shared__ u32 sh[16];
-	__shared__ ElemT s_key[15];
-	__shared__ u64 s_idx[15];
-	if (threadIdx.x < 16) sh[threadIdx.x] = 0;
-	if (threadIdx.x < sp.count) {
-		s_key[threadIdx.x] = reinterpret_cast<const ElemT*>(sp.keys)[threadIdx.x];
-		s_idx[threadIdx.x] = sp.idx[threadIdx.x];
-	}
-	__syncthreads();
-	u32 local[16];
-#pragma unroll
-	for (int b = 0; b < 16; ++b) local[b] = 0;
-	for (size_t i = (size_t) blockIdx.x * THREADS + threadIdx.x; i < n; i += (size_t) gridDim.x * THREADS) {
-		const ElemT k = __ldcs(in + i);
-		const u64 g = sp.gidx0 + i;
-		u32 b = 0;
-		for (u32 s = 0; s < sp.count; ++s)
-			if (s_key[s] < k || (s_key[s] == k && s_idx[s] <= g)) ++b;
-#pragma unroll
-		for (int q = 0; q < 16; ++q) if (q == (int) b) local[q]++;
-	}
-#pragma unroll
-	for (int b = 0; b < 16; ++b) {
-		const u32 t = warp_reduce_sum<u32>(local[b]);
-		if ((threadIdx.x & 31) == 0 && t) atomicAdd(&sh[b], t);
-	}
-	__syncthreads();
-	if (threadIdx.x < 16 && sh[threadIdx.x]) atomicAdd(&ghist[threadIdx.x], (u64) sh[threadIdx.x]);
-}
-
-/* bins_base[b] = exclusive scan of the bucket counts; counts_out[b] = count */
-__global__ void clo_partition_scan_bins(const u64* __restrict__ ghist, u64* __restrict__ bins_base,
-		u64* __restrict__ counts_out, u32 nparts) {
-	if (threadIdx.x == 0 && blockIdx.x == 0) {
-		u64 run = 0;
-		for (u32 b = 0; b < (u32) RADIX; ++b) {
-			const u64 c = b < 16 ? ghist[b] : 0;
-			bins_base[b] = run;
-			run += c;
-			if (b < nparts && counts_out) counts_out[b] = c;
-		}
-	}
-}
-
-template <typename ElemT, bool HAS_VAL>
-cudaError_t partition_typed(CloRadixState* st, const ElemT* in, const u32* vin, ElemT* out, u32* vout, size_t n,
-		u64 gidx0, const void* sk, const u64* si, u32 nparts, u64* counts_out, cudaStream_t stream) {
-	constexpr int THREADS = TileCfg<ElemT, HAS_VAL>::THREADS;
-	constexpr int IPT = TileCfg<ElemT, HAS_VAL>::IPT;
-	constexpr size_t TILE = (size_t) THREADS * IPT;
-	constexpr size_t SMEM = onesweep_smem<ElemT, HAS_VAL, THREADS, IPT>();
-	const size_t tiles = (n + TILE - 1) / TILE;
-	const bool wide = n >= (1ull << 30);
-	WorkLayout L;
-	cudaError_t e;
-	if ((e = prepare_work(st, tiles, 1, wide ? 8 : 4, L, stream)) != cudaSuccess) return e;
-	SplitterArgs sp = { sk, si, nparts - 1, gidx0 };
-	CloKeySpec ks = {};
-	ks.identity = 1;
-	const unsigned hb = (unsigned) (tiles < 1184 ? (tiles ? tiles : 1) : 1184);
-	clo_partition_histogram<ElemT, 256><<<hb, 256, 0, stream>>>(in, n, sp, L.ghist);
-	clo_partition_scan_bins<<<1, 32, 0, stream>>>(L.ghist, L.bins, counts_out, nparts);
-	CLO_COUNT_LAUNCH(2);
-	if ((e = cudaGetLastError()) != cudaSuccess) return e;
-	if (n == 0) return cudaSuccess;
-	if (wide) {
-		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u64, THREADS, IPT, RANK_BALLOT>;
-		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
-		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u64*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err, 0);
-	} else {
-		auto kern = clo_radix_onesweep<ElemT, HAS_VAL, true, true, u32, THREADS, IPT, RANK_BALLOT>;
-		if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) SMEM)) != cudaSuccess) return e;
-		kern<<<(unsigned) tiles, THREADS, SMEM, stream>>>(in, out, vin, vout, n, (u32*) L.lookback, L.tickets, L.bins, 0, 0xff, ks, sp, L.err, 0);
-	}
-	CLO_COUNT_LAUNCH(1);
-	return cudaGetLastError();
-}
-
-} // namespace
-
 static int clo_current_sm_count() {
 	int dev = 0, sms = 0;
 	cudaGetDevice(&dev);
@@ -1002,26 +548,14 @@ cudaError_t clo_radix_partition(CloRadixState* st, size_t elem_size, const void*
 		cudaStream_t stream, const char** err_msg) {
 	if (nparts < 1 || nparts > 16) { if (err_msg) *err_msg = "partition: nparts must be in [1,16]"; return cudaErrorInvalidValue; }
 	if (n >= (1ull << 40)) { if (err_msg) *err_msg = "partition: too many elements"; return cudaErrorInvalidValue; }
-	{
-		/* default: the chunk-per-warp partition (partition.cu); CLO_PARTITION=onesweep keeps the
-		 * splitter-as-digit onesweep variant below */
-		const char* pk = getenv("CLO_PARTITION");
-		if (!(pk && strcmp(pk, "onesweep") == 0) && n < (1ull << 32)) {
-			int dev = 0, sms = 0;
-			cudaGetDevice(&dev);
-			if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
-			return clo_partition_v2(st->work, elem_size, keys_in, payload_in, keys_out, payload_out, n, gidx0,
-				splitter_keys, splitter_idx, nparts, counts_out, sms, stream, err_msg);
-		}
-	}
-	const bool has_val = payload_in != nullptr;
-	if (elem_size == 4) {
-		if (has_val) return partition_typed<u32, true>(st, (const u32*) keys_in, payload_in, (u32*) keys_out, payload_out, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
-		return partition_typed<u32, false>(st, (const u32*) keys_in, nullptr, (u32*) keys_out, nullptr, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
-	}
-	if (elem_size == 8) {
-		if (has_val) return partition_typed<u64, true>(st, (const u64*) keys_in, payload_in, (u64*) keys_out, payload_out, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
-		return partition_typed<u64, false>(st, (const u64*) keys_in, nullptr, (u64*) keys_out, nullptr, n, (u64) gidx0, splitter_keys, (const u64*) splitter_idx, nparts, (u64*) counts_out, stream);
+	if (n >= (1ull << 32)) { if (err_msg) *err_msg = "partition: at most 2^32 - 1 elements per GPU"; return cudaErrorInvalidValue; }
+	if (elem_size == 4 || elem_size == 8) {
+		/* the chunk-per-warp partition (partition.cu) */
+		int dev = 0, sms = 0;
+		cudaGetDevice(&dev);
+		if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 148;
+		return clo_partition_v2(st->work, elem_size, keys_in, payload_in, keys_out, payload_out, n, gidx0,
+			splitter_keys, splitter_idx, nparts, counts_out, sms, stream, err_msg);
 	}
 	if (err_msg) *err_msg = "partition: keys must be 4 or 8 bytes";
 	return cudaErrorInvalidValue;

@@ -437,8 +437,14 @@ extern "C" CloSort* clo_sort_new(const char* type, const char* options, CCLConte
 	const bool comparison_sort = def != &clo_sort_satradix_def;
 	/* satradix never looks at `compare` (the reference defines the macro and its radix kernels
 	 * do not use it): raw key bits ascending whatever it says */
-	const bool in_menu = parse_get_key(get_key, shift, mask) && (parse_compare(compare, desc) || !comparison_sort);
+	bool in_menu = parse_get_key(get_key, shift, mask) && (parse_compare(compare, desc) || !comparison_sort);
 	if (!comparison_sort) desc = 0;
+	/* an integer element with a float key type (or the reverse) is a VALUE conversion in the
+	 * reference, `(float) (x)`: the precompiled kernels only reinterpret bits, so these go through
+	 * the run-time compiler, which emits the real cast */
+	if (in_menu && ((kind_of(et) == CLO_KIND_FLOAT) != (kind_of(kt) == CLO_KIND_FLOAT))) {
+		in_menu = false; shift = 0; mask = ~0ull;
+	}
 	if (!ierr && !in_menu && comparison_sort) {
 		/* the reference compiles ANY macro body into its kernels (clo_sort_abstract.c:144-168);
 		 * strings outside the precompiled menu are compiled here too, with NVRTC */

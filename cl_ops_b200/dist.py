@@ -107,6 +107,8 @@ class GpuOps:
             self.cd_bufs = (self._buf(self.cd_out_k), self._buf(self.cd_out_p) if with_payload else None)
             return
         P, r = dist.get_world_size(group), dist.get_rank(group)
+        if P > 16:
+            raise ValueError("the peer exchange supports at most 16 ranks per box (got %d)" % P)
         kb = torch.empty(0, dtype=key_dtype).element_size()
         own = [self.clo.Buffer(self.ctx, size=max(1, capacity) * kb)]
         if with_payload:

@@ -34,9 +34,10 @@ typedef enum clo_rng_seed_type {
 
 /* clo_rng.in.h:97-99 / clo_rng.c:262-405.
  * `hash` (DEV_GID only) is an OpenCL C macro body in the reference
- * (clo_rng.c:101-109); accepted here: NULL, "", "x" (no hash), "KNUTH(x)",
- * "XS1(x)" (clo_rng_init.cl:29-35), and any expression without an assignment
- * (a no-op there too).  Anything else fails with CLO_ERROR_ARGS. */
+ * (clo_rng.c:101-109); precompiled here: NULL, "", "x" (no hash), "KNUTH(x)",
+ * "XS1(x)" (clo_rng_init.cl:29-35); an expression without an assignment is a
+ * no-op there too; any other string is built into the seeding kernel at run
+ * time with NVRTC (one that does not compile fails with CLO_ERROR_ARGS). */
 CloRng* clo_rng_new(const char* type, CloRngSeedType seed_type,
 	void* seeds, size_t seeds_count, cl_ulong main_seed,
 	const char* hash, CCLContext* ctx, CCLQueue* cq, GError** err);

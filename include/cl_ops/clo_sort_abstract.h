@@ -9,11 +9,12 @@
  *               identical results, honours `compare` and `get_key`.
  *   "gselect"   stable rank sort (clo_sort_gselect.cl:38-57), out of place.
  *
- * `compare` and `get_key` are OpenCL C macro bodies in the reference
- * (clo_sort_abstract.c:157-168).  Without a run-time compiler they are matched
- * against a fixed menu: compare in { NULL, "((a) > (b))", "((a) < (b))" };
- * get_key in { NULL, "(x)", "((x) >> K)", "((x) & M)", "(((x) >> K) & M)" }.
- * Anything else fails with CLO_ERROR_ARGS.
+ * `compare` and `get_key` are OpenCL C macro bodies in the reference, spliced into its kernels
+ * at build time (clo_sort_abstract.c:157-168).  Here a menu is precompiled -- compare in
+ * { NULL, "((a) > (b))", "((a) < (b))" }; get_key in { NULL, "(x)", "((x) >> K)", "((x) & M)",
+ * "(((x) >> K) & M)" } -- and ANY other string is compiled at run time with NVRTC, for all four
+ * algorithms (satradix: the key extraction; its kernels never expand `compare`).  A string that
+ * does not compile fails with CLO_ERROR_ARGS carrying the compiler log.
  */
 #ifndef CLO_B200_SORT_ABSTRACT_H
 #define CLO_B200_SORT_ABSTRACT_H

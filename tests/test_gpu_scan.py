@@ -124,6 +124,65 @@ def test_scan_large_both_kernels(clo, ctx, queue, kernel, monkeypatch):
     s.destroy()
 
 
+@pytest.mark.parametrize("et", [oracle.UINT, oracle.INT, oracle.FLOAT, oracle.ULONG, oracle.LONG, oracle.DOUBLE])
+@pytest.mark.parametrize("n", [(1 << 23) + 3 * 4096 + 32, (1 << 22), (1 << 22) + 4096 * 295 + 64])
+def test_scan_copy_engine_kernel(clo, ctx, queue, et, n, monkeypatch):
+    """clo_scan_tma (element and sum type of the same size, n a multiple of 128 bytes): TMA boxes
+    clipped by the tensor map on the ragged last tile, carry-in through the propagator chain,
+    repeated calls (epoch tags), in place, and the same bits as the cp.async kernel it replaces."""
+    import torch
+    dt = oracle.NP_TYPES[et]
+    rng = np.random.default_rng(n % 1000 + et)
+    if np.issubdtype(dt, np.integer):
+        info = np.iinfo(dt)
+        a = rng.integers(info.min, info.max, size=n, dtype=dt, endpoint=True)
+    else:
+        a = rng.random(n).astype(dt)
+    tdt = {np.uint32: torch.int32, np.int32: torch.int32, np.float32: torch.float32, np.uint64: torch.int64,
+           np.int64: torch.int64, np.float64: torch.float64}[dt]
+    sdt = {4: np.int32, 8: np.int64}[a.dtype.itemsize] if np.issubdtype(dt, np.integer) else dt
+    t_in = torch.from_numpy(a.view(sdt).copy()).cuda()
+    t_out = torch.empty(n, dtype=tdt, device="cuda")
+    carry_val = 12345 if np.issubdtype(dt, np.integer) else 1000.5
+    t_carry = torch.tensor([carry_val], dtype=tdt, device="cuda")
+    torch.cuda.synchronize()
+    b_in, b_out, b_c = (clo.Buffer.wrap_tensor(ctx, t) for t in (t_in, t_out, t_carry))
+    s = clo.CloScan("blelloch", ctx, et, et)
+    if np.issubdtype(dt, np.integer):
+        want = oracle.scan(a, et, et)
+        def check(got, carry):
+            w = (want.astype(np.uint64) + np.uint64(carry)).astype(want.dtype) if carry else want
+            assert np.array_equal(got.view(want.dtype), w)
+    else:
+        ref = np.cumsum(a.astype(np.float64)) - a.astype(np.float64)
+        def check(got, carry):
+            r = ref + carry
+            tol = (1e-5 if dt == np.float32 else 1e-12) * np.abs(r) + (1e-3 if dt == np.float32 else 1e-9)
+            assert np.all(np.abs(got.astype(np.float64) - r) <= tol)
+    for rep in range(3):
+        s.with_device_data(queue, b_in, b_out, n, carry_in=b_c if rep == 1 else None)
+        queue.finish()
+        check(t_out.cpu().numpy(), carry_val if rep == 1 else 0)
+    first = t_out.cpu().numpy().copy()
+    # the cp.async kernel gives the same bits (integers) / the same tolerance (floats)
+    monkeypatch.setenv("CLO_SCAN_KERNEL", "pp")
+    s2 = clo.CloScan("blelloch", ctx, et, et)
+    s2.with_device_data(queue, b_in, b_out, n)
+    queue.finish()
+    if np.issubdtype(dt, np.integer):
+        assert np.array_equal(t_out.cpu().numpy(), first)
+    else:
+        check(t_out.cpu().numpy(), 0)
+    s2.destroy()
+    # in place
+    s.with_device_data(queue, b_in, b_in, n)
+    queue.finish()
+    check(t_in.cpu().numpy(), 0)
+    for b in (b_in, b_out, b_c):
+        b.destroy()
+    s.destroy()
+
+
 def test_scan_errors(clo, ctx):
     with pytest.raises(clo.CloError) as ei:
         clo.CloScan("nosuchscan", ctx, oracle.UINT, oracle.UINT)

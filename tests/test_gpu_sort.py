@@ -481,6 +481,30 @@ def test_satradix_custom_get_key_is_compiled_at_run_time(clo, ctx, queue, et, kt
     s.destroy()
 
 
+@pytest.mark.parametrize("alg", ["sbitonic", "gselect"])
+def test_integer_elements_with_a_float_key_are_converted_by_value(clo, ctx, queue, alg):
+    """elem uint, key float, default get_key: the reference's kernels compute `(float) (x)` -- a
+    VALUE conversion (clo_sort_abstract.c:157-168) -- so values >= 2^31 must sort as large
+    numbers, not as negative IEEE patterns.  These type mixes go through the run-time compiler."""
+    rng = np.random.default_rng(9)
+    a = rng.integers(0, 2**32, size=4096, dtype=np.uint64).astype(np.uint32)
+    a[:8] = [0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 0, 1, 0xC0000000, 0x3F800000, 0xBF800000]
+    s = clo.CloSort(alg, ctx, oracle.UINT, key_type=oracle.FLOAT)
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    assert np.array_equal(np.sort(got), np.sort(a))                 # a permutation
+    k = got.astype(np.float32)                                      # the key the kernels compared
+    assert np.all(k[1:] >= k[:-1])
+    # and the reverse: float elements ordered by their truncated integer value
+    f = ((rng.random(2048) - 0.5) * 1000).astype(np.float32)
+    s = clo.CloSort(alg, ctx, oracle.FLOAT, key_type=oracle.INT)
+    got = s.with_host_data(f, queue)
+    s.destroy()
+    assert np.array_equal(np.sort(got), np.sort(f))
+    ki = np.trunc(got).astype(np.int64)
+    assert np.all(ki[1:] >= ki[:-1])
+
+
 def test_introspection_getters_name_real_kernels(clo, ctx):
     """clo_sort_get_kernel_name / clo_scan_get_kernel_name (clo_sort_abstract.c:571-629) return the
     names of CUDA kernels that exist in the library, the counts of the per-algorithm headers, and
