@@ -231,7 +231,23 @@ clo_scan_reduce_partial(const ElemT* __restrict__ in, size_t n, typename AccOf<S
 	const size_t nvec = n / EPV;
 	const bool vec_ok = (reinterpret_cast<uintptr_t>(in) % (sizeof(ElemT) * EPV)) == 0;
 	if (vec_ok) {
-		for (size_t i = (size_t) blockIdx.x * THREADS + threadIdx.x; i < nvec; i += (size_t) gridDim.x * THREADS) {
+		/* four independent 16-byte loads per thread and step; a step's 4 * EPV elements are summed in
+		 * the tile-local type (f32 for f32 sums, like the scan kernels) before they join the f64 total */
+		typedef typename std::conditional<std::is_same<SumT, float>::value, float, AccT>::type IntraT;
+		const size_t stride = (size_t) gridDim.x * THREADS;
+		size_t i = (size_t) blockIdx.x * THREADS + threadIdx.x;
+		for (; i + 3 * stride < nvec; i += 4 * stride) {
+			ElemT e[4][EPV];
+#pragma unroll
+			for (int u = 0; u < 4; ++u) load_vec_cs<ElemT, EPV>(in + (i + u * stride) * EPV, e[u]);
+			IntraT part = IntraT(0);
+#pragma unroll
+			for (int u = 0; u < 4; ++u)
+#pragma unroll
+				for (int c = 0; c < EPV; ++c) part += to_acc<ElemT, SumT, IntraT>(e[u][c]);
+			acc += static_cast<AccT>(part);
+		}
+		for (; i < nvec; i += stride) {
 			ElemT e[EPV];
 			load_vec_cs<ElemT, EPV>(in + i * EPV, e);
 #pragma unroll

@@ -21,6 +21,7 @@ struct clo_sort {
 	/* backend */
 	CloKeySpec ks;
 	unsigned radix;          /* satradix "radix=" option (clo_sort_satradix.c:352,385-392) */
+	int typed_order;         /* satradix "typed_order=1": opt-in numeric order for signed / float keys */
 	unsigned minps, maxps, maxsfs;  /* abitonic options: maxps / maxsfs set the fusion depth of the bitonic kernel */
 	CloRadixState* rs;
 	CloBitonicState* bs;
@@ -111,6 +112,7 @@ static bool next_option(const char*& p, std::string& key, std::string& val, bool
 
 static const char* satradix_init(CloSort* sorter, const char* options, GError** err) {
 	sorter->radix = 16;
+	sorter->typed_order = 0;
 	if (options) {
 		const char* p = options;
 		std::string k, v; bool bad;
@@ -125,6 +127,11 @@ static const char* satradix_init(CloSort* sorter, const char* options, GError** 
 					g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "Radix must be a power of 2.");
 					return NULL;
 				}
+			} else if (k == "typed_order") {
+				/* not in the reference, which sorts raw key bits whatever the key type
+				 * (clo_sort_satradix.cl:61: negative ints after positive ones, floats by bit
+				 * pattern).  Opt-in: order signed integers and floats by VALUE. */
+				sorter->typed_order = atoi(v.c_str()) != 0;
 			} else if (k.size() >= 4 && strncasecmp(k.c_str(), "scan", 4) == 0) {
 				/* the reference forwards these to its internal scanner
 				 * (clo_sort_satradix.c:393-406); the onesweep has no scan kernel.
@@ -176,12 +183,50 @@ static bool satradix_sorted_bits(CloSort* sorter, uint32_t& bits, GError** err) 
 	return true;
 }
 
+/* typed_order: a bijection on the key bits that turns numeric order into unsigned order (sign
+ * bit flipped for signed integers; floats: all bits of negatives, the sign bit of the others)
+ * and its inverse, applied around the raw-bit passes */
+template <typename U, bool IS_FLOAT, bool INVERSE>
+__global__ void clo_radix_typed_flip(const U* __restrict__ in, U* __restrict__ out, size_t n) {
+	const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const U sign = (U) 1 << (8 * sizeof(U) - 1);
+	U k = in[i];
+	if (!IS_FLOAT) k ^= sign;
+	else if (!INVERSE) k ^= (k & sign) ? (U) ~(U) 0 : sign;
+	else k ^= (k & sign) ? sign : (U) ~(U) 0;
+	out[i] = k;
+}
+
+template <typename U>
+static void typed_flip(bool is_float, bool inverse, const void* in, void* out, size_t n, cudaStream_t stream) {
+	const unsigned grid = (unsigned) ((n + 255) / 256);
+	if (!is_float) clo_radix_typed_flip<U, false, false><<<grid, 256, 0, stream>>>((const U*) in, (U*) out, n);
+	else if (!inverse) clo_radix_typed_flip<U, true, false><<<grid, 256, 0, stream>>>((const U*) in, (U*) out, n);
+	else clo_radix_typed_flip<U, true, true><<<grid, 256, 0, stream>>>((const U*) in, (U*) out, n);
+	CLO_COUNT_LAUNCH(1);
+}
+
+static void typed_flip_any(size_t es, bool is_float, bool inverse, const void* in, void* out, size_t n, cudaStream_t stream) {
+	switch (es) {
+	case 1: typed_flip<unsigned char>(false, inverse, in, out, n, stream); break;
+	case 2: typed_flip<unsigned short>(false, inverse, in, out, n, stream); break;
+	case 4: typed_flip<unsigned int>(is_float, inverse, in, out, n, stream); break;
+	default: typed_flip<unsigned long long>(is_float, inverse, in, out, n, stream); break;
+	}
+}
+
 static CCLEvent* satradix_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exec, CCLQueue* cq_comm,
 		CCLBuffer* data_in, CCLBuffer* data_out, size_t numel, size_t lws_max, GError** err) {
 	(void) cq_comm; (void) lws_max;
 	if ((err && *err) || !cq_exec) return NULL;
 	if (!check_buffers(sorter, data_in, data_out, numel, err)) return NULL;
-	if (sorter->ks.key_kind == CLO_KIND_FLOAT) {
+	const bool typed = sorter->typed_order && sorter->ks.key_kind != CLO_KIND_UNSIGNED;
+	if (typed && (sorter->jit || !sorter->ks.identity || sorter->key_type != sorter->elem_type)) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "satradix typed_order needs the identity key (key type = element type, get_key (x))");
+		return NULL;
+	}
+	if (sorter->ks.key_kind == CLO_KIND_FLOAT && !typed) {
 		/* `key >> b` does not compile for a float key in OpenCL C
 		 * (clo_sort_satradix.cl:61): the reference fails at build time */
 		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "satradix sorts integer keys only");
@@ -193,6 +238,19 @@ static CCLEvent* satradix_sort_with_device_data(CloSort* sorter, CCLQueue* cq_ex
 	ccl_event* evt = clo_queue_begin(cq_exec, "clo_radix_onesweep");
 	const char* msg = NULL;
 	void* dst = data_out ? data_out->ptr : data_in->ptr;
+	if (typed) {
+		/* flip -> raw-bit passes in place -> flip back */
+		const size_t es = clo_type_sizeof(sorter->elem_type);
+		const bool is_float = sorter->ks.key_kind == CLO_KIND_FLOAT;
+		typed_flip_any(es, is_float, false, data_in->ptr, dst, numel, cq_exec->stream);
+		cudaError_t rc2 = clo_radix_sort(sorter->rs, clo_sm_count(cq_exec->ctx->dev.ordinal), es, sorter->ks,
+			(uint32_t) (8 * es), dst, dst, NULL, NULL, numel, cq_exec->stream, &msg);
+		if (rc2 == cudaSuccess) { typed_flip_any(es, is_float, true, dst, dst, numel, cq_exec->stream); rc2 = cudaGetLastError(); }
+		clo_queue_end(cq_exec, evt);
+		if (rc2 != cudaSuccess && msg) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "%s", msg); return NULL; }
+		if (clo_cuda_failed(rc2, err, "clo_radix_sort (typed order)")) return NULL;
+		return evt;
+	}
 	cudaError_t rc = sorter->jit
 		? clo_jit_radix_sort(sorter->jit, sorter->rs, clo_sm_count(cq_exec->ctx->dev.ordinal),
 			clo_type_sizeof(sorter->elem_type), clo_type_sizeof(sorter->key_type), bits, data_in->ptr, dst, numel, cq_exec->stream, &msg)

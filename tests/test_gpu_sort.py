@@ -505,6 +505,33 @@ def test_integer_elements_with_a_float_key_are_converted_by_value(clo, ctx, queu
     assert np.all(ki[1:] >= ki[:-1])
 
 
+@pytest.mark.parametrize("et", [oracle.CHAR, oracle.SHORT, oracle.INT, oracle.LONG, oracle.FLOAT, oracle.DOUBLE])
+@pytest.mark.parametrize("n", [1, 1000, (1 << 18) + 77])
+def test_satradix_typed_order_opt_in(clo, ctx, queue, et, n):
+    """options "typed_order=1" (an opt-in deviation): signed integers and floats in
+    numeric order.  Without it the reference's raw-bit order stays (negative ints after positive
+    ones) and float keys are rejected, as `key >> b` does not compile for them."""
+    rng = np.random.default_rng(n + et)
+    a = _rand(rng, et, n)
+    if a.dtype.kind == "f" and n >= 8:
+        a[:4] = [np.inf, -np.inf, 0.0, np.finfo(a.dtype).tiny]
+    s = clo.CloSort("satradix", ctx, et, options="typed_order=1")
+    got = s.with_host_data(a, queue)
+    s.destroy()
+    assert np.array_equal(got, np.sort(a))
+    if a.dtype.kind == "i":
+        s = clo.CloSort("satradix", ctx, et)                       # the reference's order: raw bits
+        got = s.with_host_data(a, queue)
+        s.destroy()
+        u = a.view({1: np.uint8, 2: np.uint16, 4: np.uint32, 8: np.uint64}[a.dtype.itemsize])
+        assert np.array_equal(got.view(u.dtype), np.sort(u))
+    else:
+        s = clo.CloSort("satradix", ctx, et)
+        with pytest.raises(clo.CloError):
+            s.with_host_data(a, queue)
+        s.destroy()
+
+
 def test_introspection_getters_name_real_kernels(clo, ctx):
     """clo_sort_get_kernel_name / clo_scan_get_kernel_name (clo_sort_abstract.c:571-629) return the
     names of CUDA kernels that exist in the library, the counts of the per-algorithm headers, and
