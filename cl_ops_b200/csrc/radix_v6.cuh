@@ -432,6 +432,8 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 	int s0 = 0, s1 = 2, s2 = 1;       /* s_ds slots of cur, t1, t2 (k, k-1, k-2 mod 3) */
 	const LbT zero_w[DPT] = {};
 	constexpr int WO_T = THREADS - DT;        /* threads of the overlapped write-out */
+	/* a tile is HEAVY when one digit holds >= TILE >> hv_shift keys (1/8; flags bits 8-9: 1/16, 1/4, 1/32 for A/B) */
+	const int hv_shift = ((flags >> 8) & 3) == 0 ? 3 : (((flags >> 8) & 3) == 1 ? 4 : (((flags >> 8) & 3) == 2 ? 2 : 5));
 	bool lumpy = false;                       /* the last counted tile has a digit with >= 1/64 of its keys */
 	bool heavy = false;                       /* ... with >= 1/8 of its keys ... */
 	u32 heavy_digit = 0;                      /* ... this one */
@@ -519,7 +521,7 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 		mark(3);
 		const u32 nxt2 = s_misc[8];
 		const bool more = nxt < num_tiles;
-		heavy = (s_misc[16] >> 8) >= (u32) (TILE / 8);
+		heavy = (s_misc[16] >> 8) >= ((u32) TILE >> hv_shift);
 		lumpy = (s_misc[16] >> 8) >= (u32) (TILE / 64);
 		heavy_digit = s_misc[16] & 0xffu;
 		if (nxt2 < num_tiles) {
