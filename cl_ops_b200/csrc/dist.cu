@@ -44,13 +44,18 @@ __global__ void clo_dist_sample(const void* __restrict__ keys, u64 numel, u32 ca
  * as (key, index RELATIVE to this rank's first element, clamped at 0): with them the partition
  * kernels run with gidx0 = 0 and the host never needs the global offsets.  info[0] = this rank's
  * global offset, info[1] = total number of elements. */
-__global__ void clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 cap, u32 rank, u64 gidx0_given,
+__global__ void __launch_bounds__(256)
+clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 cap, u32 rank, u64 gidx0_given,
 		int kb, void* __restrict__ spl_keys, u64* __restrict__ spl_idx, u64* __restrict__ info) {
-	__shared__ u64 s_keys[256];
-	__shared__ unsigned char s_valid[256];
+	/* a CTA ranks 32 samples; its 8 warps each compare them with one eighth of every 2048-slot tile */
+	constexpr int TILE = 2048;
+	__shared__ u64 s_keys[TILE];
+	__shared__ unsigned char s_valid[TILE];
+	__shared__ u32 s_part[8][32];
 	__shared__ u64 s_g0[DIST_MAX_WORLD + 1];
 	__shared__ u32 s_cnt[DIST_MAX_WORLD + 1];
 	const u32 row_w = 2 + cap;
+	const u32 lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
 	if (threadIdx.x == 0) {
 		u64 g = 0; u32 c = 0;
 		for (u32 r = 0; r < world; ++r) { s_g0[r] = g; s_cnt[r] = c; g += all[(size_t) r * row_w]; c += (u32) all[(size_t) r * row_w + 1]; }
@@ -59,30 +64,37 @@ __global__ void clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 c
 	__syncthreads();
 	const u32 total = s_cnt[world];
 	const u32 slots = world * cap;
-	const u32 me = blockIdx.x * blockDim.x + threadIdx.x;
+	const u32 me = blockIdx.x * 32 + lane;
 	const u32 my_r = me / cap, my_j = me % cap;
 	const bool valid = me < slots && my_j < (u32) all[(size_t) my_r * row_w + 1];
 	const u64 my_key = valid ? all[(size_t) my_r * row_w + 2 + my_j] : 0ull;
 	u32 below = 0;
-	for (u32 base = 0; base < slots; base += 256) {
-		const u32 o = base + threadIdx.x;
-		const u32 r = o / cap, j = o % cap;
-		const bool v = o < slots && j < (u32) all[(size_t) r * row_w + 1];
+	for (u32 base = 0; base < slots; base += TILE) {
 		__syncthreads();
-		s_keys[threadIdx.x] = v ? all[(size_t) r * row_w + 2 + j] : ~0ull;
-		s_valid[threadIdx.x] = v ? 1 : 0;            /* an empty slot never counts */
+		for (u32 i = threadIdx.x; i < (u32) TILE; i += 256) {
+			const u32 o = base + i;
+			const u32 r = o / cap, j = o % cap;
+			const bool v = o < slots && j < (u32) all[(size_t) r * row_w + 1];
+			s_keys[i] = v ? all[(size_t) r * row_w + 2 + j] : ~0ull;
+			s_valid[i] = v ? 1 : 0;                    /* an empty slot never counts */
+		}
 		__syncthreads();
 		if (valid) {
-			const u32 lim = min(256u, slots - base);
+			const u32 t0 = slice * (TILE / 8);
 #pragma unroll 8
-			for (u32 t = 0; t < lim; ++t) {
+			for (u32 t = t0; t < t0 + TILE / 8; ++t) {
 				const u64 k = s_keys[t];
 				below += (s_valid[t] && (k < my_key || (k == my_key && base + t < me))) ? 1u : 0u;
 			}
 		}
 	}
-	if (me == 0) { info[0] = gidx0_given != ~0ull ? gidx0_given : s_g0[rank]; info[1] = s_g0[world]; }
-	if (!valid || total == 0) return;
+	s_part[slice][lane] = below;
+	__syncthreads();
+	if (blockIdx.x == 0 && threadIdx.x == 0) { info[0] = gidx0_given != ~0ull ? gidx0_given : s_g0[rank]; info[1] = s_g0[world]; }
+	if (slice != 0 || !valid || total == 0) return;
+	below = 0;
+#pragma unroll
+	for (int w = 0; w < 8; ++w) below += s_part[w][lane];
 	const u64 my_g0 = gidx0_given != ~0ull ? gidx0_given : s_g0[rank];
 	for (u32 k = 1; k < world; ++k) {
 		const u32 pick = (u32) (((u64) k * total) / world);
@@ -367,9 +379,8 @@ extern "C" cl_bool clo_dist_sort_with_device_data(CloDist* d, CCLQueue* cq, CCLB
 	}
 	mark();
 	/* 2) splitters */
-	cudaMemsetAsync(d->b_splk->ptr, 0, DIST_MAX_WORLD * 8, st);
-	cudaMemsetAsync(d->b_spli->ptr, 0, DIST_MAX_WORLD * 8, st);
-	clo_dist_splitters<<<(P * cap + 255) / 256, 256, 0, st>>>(d->d_all, P, cap, r, (u64) gidx0, d->kb, d->b_splk->ptr,
+	cudaMemsetAsync(d->b_splk->ptr, 0, 2 * DIST_MAX_WORLD * 8, st);     /* keys and indices are adjacent */
+	clo_dist_splitters<<<(P * cap + 31) / 32, 256, 0, st>>>(d->d_all, P, cap, r, (u64) gidx0, d->kb, d->b_splk->ptr,
 		(u64*) d->b_spli->ptr, d->d_info);
 	CLO_COUNT_LAUNCH(1);
 	mark();
