@@ -403,8 +403,15 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 
 	/* ping-pong chain that ends in dst without touching src (unless in place):
 	 * odd number of passes: src->dst->aux->dst...; even: src->aux->dst->aux->dst */
+	/* chain mode (every pass runs the v6 kernel): a pass whose digit is the same for every key --
+	 * small keys, sorted prefixes, all-equal input -- moves nothing; the passes hand the location of
+	 * the keys on through 16-byte chain words and one conditional copy at the end puts the result
+	 * into dst.  Flag 128 keeps the round-1 behaviour (identity pass = copy) for A/B. */
+	bool chain_mode = false;
+	if constexpr (IDENTITY && sizeof(ElemT) >= 4 && THREADS > RADIX) chain_mode = st->kernel_v6 && !(g_pp_flags & 128);
+	char* chain = (char*) L.tickets + 64;                     /* [MAX_PASSES + 1] chain words behind the tickets */
 	const ElemT* cur = src; const u32* vcur = vsrc;
-	if ((const void*) src == (const void*) dst && (cfg.passes & 1)) {
+	if (!chain_mode && (const void*) src == (const void*) dst && (cfg.passes & 1)) {
 		/* in place with an odd number of passes: start the chain from the aux copy */
 		if ((e = cudaMemcpyAsync(aux, src, n * sizeof(ElemT), cudaMemcpyDeviceToDevice, stream)) != cudaSuccess) return e;
 		cur = aux;
@@ -423,6 +430,13 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 			if (st->kernel_v6) {
 				char* agg = (char*) st->pp.ptr;
 				char* pref = agg + tiles * RADIX * (wide ? 8 : 4);
+				if (chain_mode) {
+					ElemT* alt = to_dst ? aux : dst;
+					u32* valt = to_dst ? vaux : vdst;
+					e = clo_radix_v6_pass((int) sizeof(ElemT), wide ? 1 : 0, THREADS * IPT, src, nxt, HAS_VAL ? vsrc : nullptr, HAS_VAL ? vnxt : nullptr, n, agg, pref, ticket,
+						L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], L.err, sm_count, g_radix_profile, g_pp_flags, stream,
+						p == 0 ? nullptr : chain + 16 * p, chain + 16 * (p + 1), alt, HAS_VAL ? valt : nullptr);
+				} else
 				e = clo_radix_v6_pass((int) sizeof(ElemT), wide ? 1 : 0, THREADS * IPT, cur, nxt, HAS_VAL ? vcur : nullptr, HAS_VAL ? vnxt : nullptr, n, agg, pref, ticket,
 					L.bins + p * RADIX, cfg.start_bit[p], cfg.dmask[p], L.err, sm_count, g_radix_profile, g_pp_flags, stream);
 				done_v6 = true;
@@ -447,6 +461,8 @@ cudaError_t radix_sort_cfg(CloRadixState* st, int sm_count, const CloKeySpec& ks
 		st->mark(stream);
 		cur = nxt; vcur = vnxt;
 	}
+	if (chain_mode && cfg.passes > 0)
+		return clo_radix_v6_chain_fixup(chain + 16 * cfg.passes, dst, HAS_VAL ? (void*) vdst : nullptr, n * sizeof(ElemT), n * sizeof(u32), sm_count, stream);
 	return cudaSuccess;
 }
 

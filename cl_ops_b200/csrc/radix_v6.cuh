@@ -44,6 +44,31 @@
 #ifndef CLO_RADIX_V6_CUH
 #define CLO_RADIX_V6_CUH
 
+/* location of the keys (and payloads) between two passes of one sort */
+struct V6Chain { const void* cur; const void* vcur; };
+
+/* after the last pass: the result belongs in dst; copies only when data-dependent skipping left
+ * it elsewhere (16 bytes per thread and step; buffers from cudaMalloc are always aligned) */
+__global__ void __launch_bounds__(512)
+clo_radix_chain_fixup(const V6Chain* __restrict__ chain, void* __restrict__ dst, void* __restrict__ vdst, size_t key_bytes, size_t val_bytes) {
+	auto copy = [&](const void* src, void* to, size_t bytes) {
+		if (src == (const void*) to || bytes == 0) return;
+		const size_t w = (size_t) blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t) gridDim.x * blockDim.x;
+		if (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(to)) & 15) == 0) {
+			const size_t nv = bytes / 16;
+			for (size_t i = w; i < nv; i += stride)
+				__stcs(reinterpret_cast<uint4*>(to) + i, __ldcs(reinterpret_cast<const uint4*>(src) + i));
+			for (size_t i = nv * 16 + w; i < bytes; i += stride)
+				reinterpret_cast<unsigned char*>(to)[i] = reinterpret_cast<const unsigned char*>(src)[i];
+		} else {
+			for (size_t i = w; i < bytes; i += stride)
+				reinterpret_cast<unsigned char*>(to)[i] = reinterpret_cast<const unsigned char*>(src)[i];
+		}
+	};
+	copy(chain->cur, dst, key_bytes);
+	if (vdst) copy(chain->vcur, vdst, val_bytes);
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 	asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(threads) : "memory");
 }
@@ -115,11 +140,22 @@ __host__ __device__ constexpr int v6_num_prop(int threads, int word_bytes) { ret
 
 template <typename ElemT, typename LbT, int THREADS, int IPT, bool HAS_VAL = false, bool VERIFY = true>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 384 ? 3 : 2))
-clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
-		const u32* __restrict__ vin, u32* __restrict__ vout, size_t n, u32 num_tiles,
+clo_radix_onesweep_v6(const ElemT* in_arg, ElemT* out_arg,
+		const u32* vin_arg, u32* vout_arg, size_t n, u32 num_tiles,
 		LbT* __restrict__ agg, LbT* __restrict__ pref, u32* __restrict__ ticket,
 		const u64* __restrict__ bins_base, u32 start_bit, u32 dmask,
-		int* __restrict__ err_flag, int prof_on, int flags) {
+		int* __restrict__ err_flag, int prof_on, int flags,
+		const V6Chain* __restrict__ chain_in, V6Chain* __restrict__ chain_out, ElemT* out_alt, u32* vout_alt) {
+	/* Where the keys are.  A pass whose digit is the same for every key moves nothing, so which
+	 * buffer holds the keys after p passes depends on the data: the launcher gives every pass
+	 * the output it would use if all passes were real (out_arg) and the other buffer (out_alt);
+	 * the pass reads the current location from the chain word its predecessor wrote, sorts into
+	 * whichever of the two it is not reading, and tells its successor (block 0).  chain_in ==
+	 * NULL: the first pass, or a caller that still moves the keys itself (identity = copy). */
+	const ElemT* __restrict__ in = chain_in ? (const ElemT*) chain_in->cur : in_arg;
+	const u32* __restrict__ vin = chain_in ? (const u32*) chain_in->vcur : vin_arg;
+	ElemT* __restrict__ out = ((const void*) out_arg == (const void*) in && out_alt) ? out_alt : out_arg;
+	u32* __restrict__ vout = ((const void*) out_arg == (const void*) in && out_alt) ? vout_alt : vout_arg;
 	constexpr int WARPS = THREADS / 32;
 	constexpr int TILE = THREADS * IPT;
 	constexpr u32 NONE = 0xffffffffu;
@@ -146,6 +182,11 @@ clo_radix_onesweep_v6(const ElemT* __restrict__ in, ElemT* __restrict__ out,
 			if (hi - bins_base[threadIdx.x] == (u64) n) s_trivial = 1;
 		}
 		__syncthreads();
+		if (chain_out && blockIdx.x == 0 && threadIdx.x == 0) {
+			chain_out->cur = s_trivial ? (const void*) in : (const void*) out;
+			chain_out->vcur = s_trivial ? (const void*) vin : (const void*) vout;
+		}
+		if (s_trivial && chain_out) return;            /* nothing moves: the successor reads where we read */
 		if (s_trivial) {
 			constexpr int NP = v6_num_prop(THREADS, (int) sizeof(LbT));
 			if (blockIdx.x < NP) return;

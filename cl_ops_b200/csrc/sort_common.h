@@ -91,7 +91,12 @@ int clo_radix_status(CloRadixState* st, cudaStream_t stream);
 cudaError_t clo_radix_v6_pass(int elem_size, int wide, int tile, const void* in, void* out,
 		const uint32_t* payload_in, uint32_t* payload_out, size_t n,
 		void* agg, void* pref, uint32_t* ticket, const unsigned long long* bins, uint32_t start_bit,
-		uint32_t dmask, int* err, int sm_count, int prof_on, int flags, cudaStream_t stream);
+		uint32_t dmask, int* err, int sm_count, int prof_on, int flags, cudaStream_t stream,
+		const void* chain_in = nullptr, void* chain_out = nullptr, void* out_alt = nullptr, uint32_t* vout_alt = nullptr);
+/* the chain words (16 bytes each) say where the keys are between passes: a pass whose digit is
+ * the same for every key moves nothing; the fixup copies the result to dst only when needed */
+cudaError_t clo_radix_v6_chain_fixup(const void* chain, void* dst, void* vdst, size_t key_bytes, size_t val_bytes,
+		int sm_count, cudaStream_t stream);
 
 /* bitonic / gselect, defined in bitonic.cu */
 struct CloBitonicState;

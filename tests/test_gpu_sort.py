@@ -532,6 +532,48 @@ def test_satradix_typed_order_opt_in(clo, ctx, queue, et, n):
         s.destroy()
 
 
+@pytest.mark.parametrize("et", [oracle.UINT, oracle.ULONG])
+@pytest.mark.parametrize("shape", ["low16", "low24", "top8", "equal", "mid", "bit0"])
+@pytest.mark.parametrize("with_payload", [False, True])
+def test_satradix_identity_passes_move_nothing(clo, ctx, queue, et, shape, with_payload):
+    """Passes whose digit is the same for every key are skipped on the device (the passes hand the
+    location of the keys on through chain words, one conditional copy at the end): any subset of
+    the passes can be an identity -- leading, trailing, in the middle, all of them -- in place and
+    out of place, keys only and with a payload (stable)."""
+    import torch
+    rng = np.random.default_rng(hash(shape) % 1000 + et)
+    n = (1 << 18) + 321
+    bits = 8 * oracle.NP_TYPES[et]().itemsize
+    a = _rand(rng, et, n)
+    mask = {"low16": 0xFFFF, "low24": 0xFFFFFF, "top8": 0xFF << (bits - 8), "equal": 0, "mid": 0xFF00 << 8, "bit0": 1}[shape]
+    a = (a & a.dtype.type(mask)) | a.dtype.type(0x0100000000000000 if (bits == 64 and shape != "top8") else 0)
+    s = clo.CloSort("satradix", ctx, et)
+    sdt = np.int32 if a.dtype.itemsize == 4 else np.int64
+    if not with_payload:
+        got = s.with_host_data(a, queue)                      # out of place on the device
+        assert np.array_equal(got, np.sort(a))
+        t = torch.from_numpy(a.view(sdt).copy()).cuda()
+        torch.cuda.synchronize()
+        b = clo.Buffer.wrap_tensor(ctx, t)
+        for rep in range(2):                                  # in place, twice (second time already sorted)
+            s.with_device_data(queue, b, None, n)
+            queue.finish()
+            assert np.array_equal(t.cpu().numpy().view(a.dtype), np.sort(a))
+        b.destroy()
+    else:
+        tk = torch.from_numpy(a.view(sdt).copy()).cuda()
+        tp = torch.arange(n, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        bk, bp = clo.Buffer.wrap_tensor(ctx, tk), clo.Buffer.wrap_tensor(ctx, tp)
+        s.pairs_with_device_data(queue, bk, bp, n)
+        queue.finish()
+        order = np.argsort(a, kind="stable")
+        assert np.array_equal(tk.cpu().numpy().view(a.dtype), a[order])
+        assert np.array_equal(tp.cpu().numpy(), order.astype(np.int32))
+        bk.destroy(); bp.destroy()
+    s.destroy()
+
+
 def test_introspection_getters_name_real_kernels(clo, ctx):
     """clo_sort_get_kernel_name / clo_scan_get_kernel_name (clo_sort_abstract.c:571-629) return the
     names of CUDA kernels that exist in the library, the counts of the per-algorithm headers, and
