@@ -45,7 +45,7 @@ __global__ void clo_dist_sample(const void* __restrict__ keys, u64 numel, u32 ca
  * kernels run with gidx0 = 0 and the host never needs the global offsets.  info[0] = this rank's
  * global offset, info[1] = total number of elements. */
 __global__ void __launch_bounds__(256)
-clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 cap, u32 rank, u64 gidx0_given,
+clo_dist_splitters(const u64* __restrict__ all, u32 row_w, u32 world, u32 cap, u32 rank, u64 gidx0_given,
 		int kb, void* __restrict__ spl_keys, u64* __restrict__ spl_idx, u64* __restrict__ info) {
 	/* a CTA ranks 32 samples; its 8 warps each compare them with one eighth of every 2048-slot tile */
 	constexpr int TILE = 2048;
@@ -54,7 +54,6 @@ clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 cap, u32 rank, u6
 	__shared__ u32 s_part[8][32];
 	__shared__ u64 s_g0[DIST_MAX_WORLD + 1];
 	__shared__ u32 s_cnt[DIST_MAX_WORLD + 1];
-	const u32 row_w = 2 + cap;
 	const u32 lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
 	if (threadIdx.x == 0) {
 		u64 g = 0; u32 c = 0;
@@ -111,22 +110,67 @@ clo_dist_splitters(const u64* __restrict__ all, u32 world, u32 cap, u32 rank, u6
 /* M[src][dst] bucket sizes -> first slot of my bucket in every destination, fits flag, and for
  * the host (mapped memory): what I receive from every source, what I send to every destination,
  * the flag and the largest slice any rank receives */
-__global__ void clo_dist_slots(const u64* __restrict__ M, u32 world, u32 rank, u64 capacity,
+__global__ void clo_dist_slots(const u64* __restrict__ M, u32 mstride, u32 world, u32 rank, u64 capacity,
 		u64* __restrict__ first_slot, int* __restrict__ ok, volatile u64* __restrict__ host) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	int fits = 1;
 	u64 worst = 0;
 	for (u32 q = 0; q < world; ++q) {
 		u64 before = 0, col = 0;
-		for (u32 s = 0; s < world; ++s) { const u64 m = M[s * world + q]; if (s < rank) before += m; col += m; }
+		for (u32 s = 0; s < world; ++s) { const u64 m = M[s * mstride + q]; if (s < rank) before += m; col += m; }
 		first_slot[q] = before;
 		if (col > capacity) fits = 0;
 		if (col > worst) worst = col;
 	}
 	*ok = fits;
-	for (u32 s = 0; s < world; ++s) { host[s] = M[s * world + rank]; host[DIST_MAX_WORLD + s] = M[rank * world + s]; }
+	for (u32 s = 0; s < world; ++s) { host[s] = M[s * mstride + rank]; host[DIST_MAX_WORLD + s] = M[rank * mstride + s]; }
 	host[2 * DIST_MAX_WORLD] = (u64) fits;
 	host[2 * DIST_MAX_WORLD + 1] = worst;
+}
+
+/* ---- control plane over peer memory.
+ * The bookkeeping collectives (sample rows, bucket sizes, per-GPU totals, "my writes have landed")
+ * are a few hundred bytes each; as NCCL calls they cost 40-150 us apiece at 8 GPUs, most of it
+ * launch and host latency.  Every rank owns a small CONTROL buffer that all peers map (CUDA IPC):
+ *   bcast: one CTA copies this rank's words into slot [rank] of every peer's buffer, fences at
+ *          system scope, and stores the call's epoch into flag [rank] of every peer;
+ *   wait:  one CTA spins (bounded) until its own flags of all ranks carry the epoch.
+ * A kernel boundary separates the wait from the consumer, so the consumer's loads cannot hit
+ * stale L1 lines.  Slots are reused by the next call only after that call's own flags, which a
+ * rank publishes after it consumed the previous ones. */
+const int CTL_ROW_MAX = 2 + 64 * DIST_MAX_WORLD;          /* words of a sample row */
+const size_t CTL_ROWS = 0;                                  /* [16][CTL_ROW_MAX] */
+const size_t CTL_SIZES = CTL_ROWS + (size_t) DIST_MAX_WORLD * CTL_ROW_MAX;    /* [16][16] */
+const size_t CTL_TOTALS = CTL_SIZES + DIST_MAX_WORLD * DIST_MAX_WORLD;        /* [2][16]: by epoch parity (a scan has no closing barrier) */
+const size_t CTL_FLAGS = CTL_TOTALS + 2 * DIST_MAX_WORLD;                     /* [4][16] */
+const size_t CTL_WORDS = CTL_FLAGS + 4 * DIST_MAX_WORLD;
+enum { CTL_F_ROWS = 0, CTL_F_SIZES = 1, CTL_F_DONE = 2, CTL_F_TOTALS = 3 };
+
+__global__ void __launch_bounds__(1024)
+clo_dist_bcast(const u64* __restrict__ src, u32 nwords, u64* const* __restrict__ ctl_ptrs, u32 world, u32 rank,
+		size_t slot_off, u32 flag, u64 epoch) {
+	for (u32 p = 0; p < world; ++p) {
+		u64* dst = ctl_ptrs[p] + slot_off;
+		for (u32 i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if (threadIdx.x < world) {
+		volatile u64* f = ctl_ptrs[threadIdx.x] + CTL_FLAGS + (size_t) flag * DIST_MAX_WORLD + rank;
+		*f = epoch;
+	}
+}
+
+__global__ void clo_dist_wait(const u64* __restrict__ ctl, u32 world, u32 flag, u64 epoch, int* __restrict__ err) {
+	if (threadIdx.x < world) {
+		const volatile u64* f = ctl + CTL_FLAGS + (size_t) flag * DIST_MAX_WORLD + threadIdx.x;
+		const long long t0 = clock64();
+		while (*f < epoch) {
+			if (clock64() - t0 > 8000000000ll) { atomicExch(err, 1); break; }      /* ~4 s: a peer never arrived */
+			__nanosleep(200);
+		}
+	}
+	__threadfence_system();
 }
 
 /* carry-in of rank `rank` from the gathered per-rank totals, in the scan's sum arithmetic */
@@ -160,6 +204,12 @@ struct clo_dist {
 	u64 *d_row = nullptr, *d_all = nullptr, *d_M = nullptr, *d_info = nullptr, *d_tot = nullptr, *d_tots = nullptr, *d_carry = nullptr;
 	u64* h_vec = nullptr;                         /* pinned, mapped: [recv x16 | send x16 | fits | worst] */
 	u64* h_vec_dev = nullptr;
+	/* control plane over peer memory (NULL: the communicator's device collectives are used) */
+	CCLBuffer* ctl = nullptr;
+	std::vector<CCLBuffer*> ctl_peers;
+	u64** d_ctl_ptrs = nullptr;                   /* device array [16] of every rank's control buffer */
+	int* d_err = nullptr;
+	u64 epoch = 0;
 	bool timing = false;
 	cudaEvent_t ev[DIST_PHASES + 1] = {};
 	bool ev_valid = false;
@@ -194,9 +244,14 @@ static void dist_release(CloDist* d) {
 }
 
 extern "C" CloDist* clo_dist_new(CCLContext* ctx, const CloDistComm* comm, GError** err) {
-	if (!ctx || !comm || !comm->all_gather_dev || !comm->barrier_dev || comm->world < 1 ||
-			comm->world > (cl_uint) DIST_MAX_WORLD || comm->rank >= comm->world) {
-		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "clo_dist_new: a communicator with 1..%d ranks and its callbacks are required", DIST_MAX_WORLD);
+	if (!ctx || !comm || comm->world < 1 || comm->world > (cl_uint) DIST_MAX_WORLD || comm->rank >= comm->world) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "clo_dist_new: a communicator with 1..%d ranks is required", DIST_MAX_WORLD);
+		return NULL;
+	}
+	const char* cm = getenv("CLO_DIST_CTRL");
+	const bool want_peer = comm->world > 1 && comm->all_gather_host && !(cm && strcmp(cm, "nccl") == 0);
+	if (comm->world > 1 && !want_peer && (!comm->all_gather_dev || !comm->barrier_dev)) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "clo_dist_new: the communicator needs all_gather_host (control plane over peer memory) or all_gather_dev + barrier_dev");
 		return NULL;
 	}
 	CloDist* d = new clo_dist();
@@ -206,9 +261,50 @@ extern "C" CloDist* clo_dist_new(CCLContext* ctx, const CloDistComm* comm, GErro
 	CloDeviceGuard g(ctx->dev.ordinal);
 	/* scan work words (the sort's area comes with clo_dist_sort_setup) */
 	void* p = nullptr;
-	if (clo_cuda_failed(cudaMalloc(&p, 8 * (2 + DIST_MAX_WORLD)), err, "clo_dist_new")) { ccl_context_unref(ctx); delete d; return NULL; }
+	if (clo_cuda_failed(cudaMalloc(&p, 8 * (4 + DIST_MAX_WORLD)), err, "clo_dist_new")) { ccl_context_unref(ctx); delete d; return NULL; }
+	cudaMemset(p, 0, 8 * (4 + DIST_MAX_WORLD));
 	d->d_tot = (u64*) p; d->d_carry = d->d_tot + 1; d->d_tots = d->d_tot + 2;
+	d->d_err = (int*) (d->d_tot + 2 + DIST_MAX_WORLD);
 	clo_handle_add(d);
+	if (want_peer) {
+		/* collective: every rank allocates its control buffer, the handles go round, every peer's is mapped */
+		const u32 P = comm->world, r = comm->rank;
+		bool ok = true;
+		d->ctl = ccl_buffer_new(ctx, 0, CTL_WORDS * 8, NULL, err);
+		ok = d->ctl != NULL;
+		if (ok) ok = !clo_cuda_failed(cudaMemset(d->ctl->ptr, 0, CTL_WORDS * 8), err, "clo_dist control buffer");
+		unsigned char mine[64] = {}, all[DIST_MAX_WORLD * 64];
+		if (ok) ok = clo_b200_ipc_export(d->ctl, mine, err) != 0;
+		/* the exchange is entered even after a local failure, so that the peers do not hang */
+		unsigned char flag_mine = ok ? 1 : 0, flags[DIST_MAX_WORLD];
+		if (comm->all_gather_host(comm->user, mine, all, 64) != 0 || comm->all_gather_host(comm->user, &flag_mine, flags, 1) != 0) ok = false;
+		for (u32 i = 0; ok && i < P; ++i) if (!flags[i]) ok = false;
+		u64 h[DIST_MAX_WORLD] = {};
+		for (u32 i = 0; ok && i < P; ++i) {
+			if (i == r) { h[i] = (u64) (uintptr_t) d->ctl->ptr; continue; }
+			CCLBuffer* b = clo_b200_ipc_import(ctx, all + (size_t) i * 64, CTL_WORDS * 8, err);
+			if (!b) { ok = false; break; }
+			d->ctl_peers.push_back(b);
+			h[i] = (u64) (uintptr_t) b->ptr;
+		}
+		if (ok) ok = !clo_cuda_failed(cudaMalloc((void**) &d->d_ctl_ptrs, sizeof(h)), err, "clo_dist control pointers");
+		if (ok) ok = !clo_cuda_failed(cudaMemcpy(d->d_ctl_ptrs, h, sizeof(h), cudaMemcpyHostToDevice), err, "clo_dist control pointers");
+		unsigned char a = ok ? 1 : 0, b2[DIST_MAX_WORLD];
+		comm->all_gather_host(comm->user, &a, b2, 1);          /* everyone is mapped (or somebody failed) */
+		for (u32 i = 0; i < P; ++i) if (!b2[i]) ok = false;
+		if (!ok) {
+			if (err && !*err) g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "clo_dist_new: setting up the peer control buffers failed on some rank");
+			/* local clean-up only: the ranks may disagree about what exists */
+			for (CCLBuffer* b : d->ctl_peers) ccl_buffer_destroy(b);
+			if (d->ctl) ccl_buffer_destroy(d->ctl);
+			if (d->d_ctl_ptrs) cudaFree(d->d_ctl_ptrs);
+			cudaFree(d->d_tot);
+			clo_handle_remove(d);
+			ccl_context_unref(ctx);
+			delete d;
+			return NULL;
+		}
+	}
 	return d;
 }
 
@@ -217,6 +313,17 @@ extern "C" void clo_dist_destroy(CloDist* d) {
 	dist_release(d);
 	{
 		CloDeviceGuard g(d->ctx->dev.ordinal);
+		if (d->ctl) {
+			/* nobody may still be writing flags into a control buffer that is about to go */
+			cudaDeviceSynchronize();
+			dist_host_barrier(d);
+			for (CCLBuffer* b : d->ctl_peers) ccl_buffer_destroy(b);
+			d->ctl_peers.clear();
+			dist_host_barrier(d);
+			ccl_buffer_destroy(d->ctl);
+			d->ctl = nullptr;
+			if (d->d_ctl_ptrs) cudaFree(d->d_ctl_ptrs);
+		}
 		cudaFree(d->d_tot);
 	}
 	ccl_context_unref(d->ctx);
@@ -374,13 +481,24 @@ extern "C" cl_bool clo_dist_sort_with_device_data(CloDist* d, CCLQueue* cq, CCLB
 	/* 1) samples -> all-gather */
 	clo_dist_sample<<<(cap + 255) / 256, 256, 0, st>>>(keys_in->ptr, (u64) numel, cap, d->kb, d->d_row);
 	CLO_COUNT_LAUNCH(1);
-	if (d->comm.all_gather_dev(d->comm.user, d->d_row, d->d_all, row_w * 8, st) != 0) {
+	const u64 epoch = ++d->epoch;
+	u64* ctl = d->ctl ? (u64*) d->ctl->ptr : nullptr;
+	const u64* all_rows = d->d_all;
+	u32 all_stride = (u32) row_w;
+	if (ctl) {
+		/* my row -> slot [rank] of every peer's control buffer; then wait for everybody's */
+		clo_dist_bcast<<<1, 1024, 0, st>>>(d->d_row, (u32) row_w, d->d_ctl_ptrs, P, r, CTL_ROWS + (size_t) r * CTL_ROW_MAX, CTL_F_ROWS, epoch);
+		clo_dist_wait<<<1, 32, 0, st>>>(ctl, P, CTL_F_ROWS, epoch, d->d_err);
+		CLO_COUNT_LAUNCH(2);
+		all_rows = ctl + CTL_ROWS;
+		all_stride = (u32) CTL_ROW_MAX;
+	} else if (d->comm.all_gather_dev(d->comm.user, d->d_row, d->d_all, row_w * 8, st) != 0) {
 		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "clo_dist_sort: all_gather_dev failed"); return CL_FALSE;
 	}
 	mark();
 	/* 2) splitters */
 	cudaMemsetAsync(d->b_splk->ptr, 0, 2 * DIST_MAX_WORLD * 8, st);     /* keys and indices are adjacent */
-	clo_dist_splitters<<<(P * cap + 31) / 32, 256, 0, st>>>(d->d_all, P, cap, r, (u64) gidx0, d->kb, d->b_splk->ptr,
+	clo_dist_splitters<<<(P * cap + 31) / 32, 256, 0, st>>>(all_rows, all_stride, P, cap, r, (u64) gidx0, d->kb, d->b_splk->ptr,
 		(u64*) d->b_spli->ptr, d->d_info);
 	CLO_COUNT_LAUNCH(1);
 	mark();
@@ -388,22 +506,40 @@ extern "C" cl_bool clo_dist_sort_with_device_data(CloDist* d, CCLQueue* cq, CCLB
 	if (!clo_sort_partition_count_with_device_data(d->sorter, cq, keys_in, numel, 0, d->b_splk, d->b_spli, P, d->b_counts, err)) return CL_FALSE;
 	mark();
 	/* 4) everybody's sizes -> where my buckets start at every destination */
-	if (d->comm.all_gather_dev(d->comm.user, d->b_counts->ptr, d->d_M, (size_t) P * 8, st) != 0) {
-		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "clo_dist_sort: all_gather_dev failed"); return CL_FALSE;
+	if (ctl) {
+		clo_dist_bcast<<<1, 32, 0, st>>>((const u64*) d->b_counts->ptr, DIST_MAX_WORLD, d->d_ctl_ptrs, P, r, CTL_SIZES + (size_t) r * DIST_MAX_WORLD, CTL_F_SIZES, epoch);
+		clo_dist_wait<<<1, 32, 0, st>>>(ctl, P, CTL_F_SIZES, epoch, d->d_err);
+		clo_dist_slots<<<1, 32, 0, st>>>(ctl + CTL_SIZES, DIST_MAX_WORLD, P, r, (u64) d->capacity, (u64*) d->b_first->ptr, (int*) d->b_ok->ptr, d->h_vec_dev);
+		CLO_COUNT_LAUNCH(3);
+	} else {
+		if (d->comm.all_gather_dev(d->comm.user, d->b_counts->ptr, d->d_M, (size_t) P * 8, st) != 0) {
+			g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "clo_dist_sort: all_gather_dev failed"); return CL_FALSE;
+		}
+		clo_dist_slots<<<1, 32, 0, st>>>(d->d_M, P, P, r, (u64) d->capacity, (u64*) d->b_first->ptr, (int*) d->b_ok->ptr, d->h_vec_dev);
+		CLO_COUNT_LAUNCH(1);
 	}
-	clo_dist_slots<<<1, 32, 0, st>>>(d->d_M, P, r, (u64) d->capacity, (u64*) d->b_first->ptr, (int*) d->b_ok->ptr, d->h_vec_dev);
-	CLO_COUNT_LAUNCH(1);
 	mark();
 	/* 5) scatter into the receive buffers of the destination ranks (a no-op unless everything fits) */
 	if (!clo_sort_partition_scatter_with_device_data(d->sorter, cq, keys_in, payload_in, numel, 0, d->b_splk, d->b_spli, P,
 			d->b_first, d->b_ptrs_k, d->with_payload ? d->b_ptrs_p : NULL, d->b_ok, err)) return CL_FALSE;
 	mark();
 	/* 6) every peer's writes have landed */
-	if (d->comm.barrier_dev(d->comm.user, st) != 0) {
+	int h_err = 0;
+	if (ctl) {
+		/* the scatter kernel has completed on this stream: fence, tell everybody, wait for everybody */
+		clo_dist_bcast<<<1, 32, 0, st>>>(nullptr, 0, d->d_ctl_ptrs, P, r, 0, CTL_F_DONE, epoch);
+		clo_dist_wait<<<1, 32, 0, st>>>(ctl, P, CTL_F_DONE, epoch, d->d_err);
+		CLO_COUNT_LAUNCH(2);
+		cudaMemcpyAsync(&h_err, d->d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+	} else if (d->comm.barrier_dev(d->comm.user, st) != 0) {
 		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "clo_dist_sort: barrier_dev failed"); return CL_FALSE;
 	}
 	if (clo_cuda_failed(cudaStreamSynchronize(st), err, "clo_dist_sort")) return CL_FALSE;     /* the one host synchronisation */
 	mark();
+	if (h_err) {
+		g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "clo_dist_sort: a peer did not arrive within the time-out (control flags)");
+		return CL_FALSE;
+	}
 	size_t n_recv = 0;
 	for (u32 i = 0; i < P; ++i) { d->last_recv[i] = d->h_vec[i]; d->last_sent[i] = d->h_vec[DIST_MAX_WORLD + i]; n_recv += (size_t) d->h_vec[i]; }
 	*numel_out = n_recv;
@@ -450,16 +586,29 @@ extern "C" CCLEvent* clo_dist_scan_with_device_data(CloDist* d, CloScan* scanner
 	cudaMemsetAsync(d->d_tot, 0, 8, st);
 	if (numel == 0 || clo_scan_reduce_with_device_data(scanner, cq, data_in, b_tot, numel, err)) {
 		/* totals travel as 8-byte words whatever the sum type (little endian: the value sits first) */
-		if (d->comm.all_gather_dev(d->comm.user, d->d_tot, d->d_tots, 8, st) != 0) {
+		const u64* tots = d->d_tots;
+		bool gathered = true;
+		if (d->ctl) {
+			const u64 epoch = ++d->epoch;
+			u64* ctl = (u64*) d->ctl->ptr;
+			/* a fast rank may already be in its NEXT scan when this one reads the totals: two slots */
+			const size_t slot = CTL_TOTALS + (size_t) (epoch & 1) * DIST_MAX_WORLD;
+			clo_dist_bcast<<<1, 32, 0, st>>>(d->d_tot, 1, d->d_ctl_ptrs, P, r, slot + r, CTL_F_TOTALS, epoch);
+			clo_dist_wait<<<1, 32, 0, st>>>(ctl, P, CTL_F_TOTALS, epoch, d->d_err);
+			CLO_COUNT_LAUNCH(2);
+			tots = ctl + slot;
+		} else if (d->comm.all_gather_dev(d->comm.user, d->d_tot, d->d_tots, 8, st) != 0) {
 			g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "clo_dist_scan: all_gather_dev failed");
-		} else {
+			gathered = false;
+		}
+		if (gathered) {
 			switch (stype) {
-			case CLO_CHAR: case CLO_UCHAR: clo_dist_carry<unsigned char, u32><<<1, 32, 0, st>>>((const unsigned char*) d->d_tots, r, (unsigned char*) d->d_carry); break;
-			case CLO_SHORT: case CLO_USHORT: clo_dist_carry<unsigned short, u32><<<1, 32, 0, st>>>((const unsigned short*) d->d_tots, r, (unsigned short*) d->d_carry); break;
-			case CLO_INT: case CLO_UINT: clo_dist_carry<u32, u32><<<1, 32, 0, st>>>((const u32*) d->d_tots, r, (u32*) d->d_carry); break;
-			case CLO_LONG: case CLO_ULONG: clo_dist_carry<u64, u64><<<1, 32, 0, st>>>((const u64*) d->d_tots, r, (u64*) d->d_carry); break;
-			case CLO_FLOAT: clo_dist_carry<float, double><<<1, 32, 0, st>>>((const float*) d->d_tots, r, (float*) d->d_carry); break;
-			case CLO_DOUBLE: clo_dist_carry<double, double><<<1, 32, 0, st>>>((const double*) d->d_tots, r, (double*) d->d_carry); break;
+			case CLO_CHAR: case CLO_UCHAR: clo_dist_carry<unsigned char, u32><<<1, 32, 0, st>>>((const unsigned char*) tots, r, (unsigned char*) d->d_carry); break;
+			case CLO_SHORT: case CLO_USHORT: clo_dist_carry<unsigned short, u32><<<1, 32, 0, st>>>((const unsigned short*) tots, r, (unsigned short*) d->d_carry); break;
+			case CLO_INT: case CLO_UINT: clo_dist_carry<u32, u32><<<1, 32, 0, st>>>((const u32*) tots, r, (u32*) d->d_carry); break;
+			case CLO_LONG: case CLO_ULONG: clo_dist_carry<u64, u64><<<1, 32, 0, st>>>((const u64*) tots, r, (u64*) d->d_carry); break;
+			case CLO_FLOAT: clo_dist_carry<float, double><<<1, 32, 0, st>>>((const float*) tots, r, (float*) d->d_carry); break;
+			case CLO_DOUBLE: clo_dist_carry<double, double><<<1, 32, 0, st>>>((const double*) tots, r, (double*) d->d_carry); break;
 			default: break;
 			}
 			CLO_COUNT_LAUNCH(1);
