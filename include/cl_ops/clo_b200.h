@@ -95,27 +95,32 @@ cl_uint clo_sort_b200_get_timing(CloSort* sorter, float* out_ms, cl_uint cap);
 /* ---- multi-GPU: one process (or thread) per GPU of one box --------------------------
  * The reference is single-device (clo_sort_abstract.c:335 takes "the first device in the
  * context"); these entry points shard its three operators over the GPUs of a box.  The
- * library moves the DATA itself (kernels that write straight into peer memory over
- * NVLink / NVSwitch, mapped with CUDA IPC); the caller supplies three tiny collectives
- * for the bookkeeping -- with NCCL each one is a single call (INTEGRATION.md has the code). */
+ * library moves everything itself over NVLink / NVSwitch through memory mapped with CUDA IPC:
+ * the DATA (the partition kernel writes every bucket straight into its destination GPU) and the
+ * bookkeeping (sample rows, bucket sizes, scan totals and the closing barrier are small kernels
+ * that write into every peer's control buffer and spin, bounded, on epoch flags).  The caller
+ * supplies ONE collective: a host all-gather that passes the 64-byte IPC handles round at
+ * set-up.  all_gather_dev / barrier_dev are optional: they carry the bookkeeping instead (one
+ * NCCL call each) when all_gather_host is missing or CLO_DIST_CTRL=nccl is set. */
 typedef struct clo_dist CloDist;
 typedef struct clo_dist_comm {
 	void* user;
 	cl_uint rank, world;                 /* world <= 16 */
-	/* device all-gather ordered on `cuda_stream`: every rank gives `bytes` bytes at send_dev and
-	 * gets world * bytes at recv_dev, in rank order (ncclAllGather).  Return 0 on success. */
+	/* optional.  Device all-gather ordered on `cuda_stream`: every rank gives `bytes` bytes at
+	 * send_dev and gets world * bytes at recv_dev, in rank order (ncclAllGather).  0 on success. */
 	int (*all_gather_dev)(void* user, const void* send_dev, void* recv_dev, size_t bytes, void* cuda_stream);
-	/* device barrier ordered on `cuda_stream`: what follows it on the stream runs after everything
-	 * the other ranks enqueued before their call has completed (a 4-byte ncclAllReduce will do) */
+	/* optional.  Device barrier ordered on `cuda_stream`: what follows it on the stream runs after
+	 * everything the other ranks enqueued before their call has completed (a 4-byte ncclAllReduce) */
 	int (*barrier_dev)(void* user, void* cuda_stream);
-	/* host all-gather, used by clo_dist_sort_setup only (the 64-byte IPC handles) */
+	/* host all-gather of `bytes` bytes per rank (set-up and tear-down only) */
 	int (*all_gather_host)(void* user, const void* send, void* recv, size_t bytes);
 } CloDistComm;
 
 #define CLO_DIST_GIDX_AUTO (~(cl_ulong) 0)
 
+/* both collective when world > 1 (the control buffers are exchanged / unmapped) */
 CloDist* clo_dist_new(CCLContext* ctx, const CloDistComm* comm, GError** err);
-void clo_dist_destroy(CloDist* d);   /* collective when clo_dist_sort_setup was called */
+void clo_dist_destroy(CloDist* d);
 
 /* Collective.  Allocates this rank's receive buffers (`capacity` elements of key_type, 4 or 8
  * bytes wide, plus cl_uint payloads when with_payload), exchanges their IPC handles and maps
