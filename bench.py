@@ -13,7 +13,8 @@ KNUTH(x) hash, main_seed 0 (bit-exact against the oracle, so the input is reprod
 
 N > 1 (under torchrun): every rank holds 2^28 keys (weak scaling); the ranks sort the
 N * 2^28 keys as one sequence with the sample sort of cl_ops_b200/dist.py (fused partition +
-peer-memory scatter over NVLink; NCCL carries only samples, bucket sizes and the barrier);
+peer-memory scatter over NVLink; samples, bucket sizes and the barrier are peer-memory writes with epoch flags,
+clo_dist_sort_with_device_data in csrc/dist.cu);
 value = all keys / max-over-ranks time.  "secondary" in the JSON line holds the other
 BASELINE.json configs measured by the same run: scans of 2^30 elements, 2^32 RNG words, the
 2^20 sbitonic sort, the 2^30 key-value sort (uniform and Zipf) and the headline sort on
@@ -652,7 +653,7 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": "satradix-equivalent LSD radix sort of 2^%d uint32 keys per GPU" % args.log2n
-                       + (" (sample sort across %d GPUs: fused partition + CUDA-IPC peer-memory scatter over NVLink; NCCL carries samples, sizes and the barrier)" % world if distributed else ""),
+                       + (" (sample sort across %d GPUs: clo_dist_sort_with_device_data: fused partition + CUDA-IPC peer-memory scatter over NVLink; samples, sizes and the barrier are peer-memory writes with epoch flags)" % world if distributed else ""),
                        "keys_per_gpu": n, "keys": "xorshift128 DEV_GID KNUTH(x) main_seed 0",
                        "api": "clo_sort_new('satradix') + clo_sort_with_device_data (out of place)",
                        "l2": "inputs (1 GiB/GPU) larger than L2, no flush", "parallelism": "sample-sort x%d" % world},
