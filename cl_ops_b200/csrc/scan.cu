@@ -661,6 +661,7 @@ struct clo_scan {
 	ScanState st;
 	ScanFn fn;
 	ReduceFn rfn;
+	CloScratch host_in, host_out;   /* device staging of clo_scan_with_host_data, kept between calls */
 };
 
 static ccl_program g_scan_program = { "clo_scan (precompiled sm_100a)", nullptr, std::string(), nullptr, {} };
@@ -809,6 +810,8 @@ extern "C" void clo_scan_destroy(CloScan* scan) {
 		scan->st.scratch.release();
 		scan->st.partials.release();
 		scan->st.pp.release();
+		scan->host_in.release();
+		scan->host_out.release();
 	}
 	ccl_context_unref(scan->ctx);
 	delete scan;
@@ -844,62 +847,52 @@ extern "C" CCLEvent* clo_scan_reduce_with_device_data(CloScan* scanner, CCLQueue
 }
 
 /* clo_scan_abstract.c:255-362: alloc in/out, H2D, scan, D2H, block */
+/* Host data in, scanned host data out (clo_scan_abstract.c:255-362: blocks until data_out is
+ * complete).  Device staging is kept in the scanner between calls; with one queue the copy in, the
+ * scan and the copy out are stream ordered and the host blocks once. */
 extern "C" cl_bool clo_scan_with_host_data(CloScan* scanner, CCLQueue* cq_exec, CCLQueue* cq_comm,
 		void* data_in, void* data_out, size_t numel, size_t lws_max, GError** err) {
 	if (!scanner || (err && *err)) return CL_FALSE;
-	cl_bool status = CL_FALSE;
-	CCLQueue* intern_queue = NULL;
-	CCLBuffer* in_dev = NULL;
-	CCLBuffer* out_dev = NULL;
-	CCLEvent* evt = NULL;
-	CCLEventWaitList ewl = NULL;
-	GError* ierr = NULL;
+	if (numel && (!data_in || !data_out)) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "scan: NULL host pointer"); return CL_FALSE; }
 	const size_t in_size = numel * clo_type_sizeof(scanner->elem_type);
 	const size_t out_size = numel * clo_type_sizeof(scanner->sum_type);
-
-	if (cq_exec == NULL) {
-		CCLDevice* dev = ccl_context_get_device(scanner->ctx, 0, &ierr);
-		if (ierr) goto error_handler;
-		intern_queue = ccl_queue_new(scanner->ctx, dev, 0, &ierr);
-		if (ierr) goto error_handler;
-		cq_exec = intern_queue;
+	CCLQueue* own_queue = NULL;
+	if (!cq_exec) {
+		own_queue = ccl_queue_new(scanner->ctx, NULL, 0, err);
+		if (!own_queue) return CL_FALSE;
+		cq_exec = own_queue;
 	}
-	if (cq_comm == NULL) cq_comm = cq_exec;
-
-	in_dev = ccl_buffer_new(scanner->ctx, CL_MEM_READ_ONLY, in_size, NULL, &ierr);
-	if (ierr) goto error_handler;
-	out_dev = ccl_buffer_new(scanner->ctx, CL_MEM_READ_WRITE, out_size, NULL, &ierr);
-	if (ierr) goto error_handler;
-
-	evt = ccl_buffer_enqueue_write(in_dev, cq_comm, CL_FALSE, 0, in_size, data_in, NULL, &ierr);
-	if (ierr) goto error_handler;
-	ccl_event_set_name(evt, "write_scan");
-	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
-	if (ierr) goto error_handler;
-
-	evt = scanner->impl_def.scan_with_device_data(scanner, cq_exec, cq_comm, in_dev, out_dev, numel, lws_max, &ierr);
-	if (ierr) goto error_handler;
-
-	evt = ccl_buffer_enqueue_read(out_dev, cq_comm, CL_FALSE, 0, out_size, data_out, ccl_ewl(&ewl, evt, NULL), &ierr);
-	if (ierr) goto error_handler;
-	ccl_event_set_name(evt, "read_scan");
-	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
-	if (ierr) goto error_handler;
-
-	if (scan_check_error_flag(scanner, cq_exec->stream, &ierr)) goto error_handler;
-	status = CL_TRUE;
-	goto finish;
-
-error_handler:
-	g_propagate_error(err, ierr);
-	status = CL_FALSE;
-
-finish:
+	if (!cq_comm) cq_comm = cq_exec;
+	const bool one_queue = cq_comm == cq_exec;
+	cl_bool ok = CL_FALSE;
+	CCLBuffer *in_dev = NULL, *out_dev = NULL;
+	CCLEventWaitList ewl = NULL;
+	{
+		CloDeviceGuard g(scanner->ctx->dev.ordinal);
+		if (clo_cuda_failed(scanner->host_in.reserve(in_size ? in_size : 1), err, "scan staging") ||
+				clo_cuda_failed(scanner->host_out.reserve(out_size ? out_size : 1), err, "scan staging")) goto done;
+		in_dev = ccl_buffer_new_wrap(scanner->ctx, scanner->host_in.ptr, in_size, err);
+		if (in_dev) out_dev = ccl_buffer_new_wrap(scanner->ctx, scanner->host_out.ptr, out_size, err);
+		if (!in_dev || !out_dev) goto done;
+		CCLEvent* evt = ccl_buffer_enqueue_write(in_dev, cq_comm, CL_FALSE, 0, in_size, data_in, NULL, err);
+		if (!evt) goto done;
+		if (!one_queue && !ccl_queue_finish(cq_comm, err)) goto done;
+		evt = scanner->impl_def.scan_with_device_data(scanner, cq_exec, cq_comm, in_dev, out_dev, numel, lws_max, err);
+		if (!evt) goto done;
+		evt = ccl_buffer_enqueue_read(out_dev, cq_comm, CL_FALSE, 0, out_size, data_out,
+			!one_queue ? ccl_ewl(&ewl, evt, NULL) : NULL, err);
+		if (!evt) goto done;
+		if (!ccl_queue_finish(cq_comm, err)) goto done;                 /* the one blocking point */
+		if (!one_queue && !ccl_queue_finish(cq_exec, err)) goto done;
+		if (scan_check_error_flag(scanner, cq_exec->stream, err)) goto done;
+		ok = CL_TRUE;
+	}
+done:
 	ccl_event_wait_list_clear(&ewl);
 	if (in_dev) ccl_buffer_destroy(in_dev);
 	if (out_dev) ccl_buffer_destroy(out_dev);
-	if (intern_queue) ccl_queue_destroy(intern_queue);
-	return status;
+	if (own_queue) ccl_queue_destroy(own_queue);
+	return ok;
 }
 
 extern "C" CCLContext* clo_scan_get_context(CloScan* s) { return s ? s->ctx : NULL; }

@@ -26,6 +26,7 @@ struct clo_sort {
 	CloRadixState* rs;
 	CloBitonicState* bs;
 	CloJitSort* jit;         /* run-time compiled network for compare / get_key strings outside the menu */
+	CloScratch host_in, host_out;   /* device staging of clo_sort_with_host_data, kept between calls */
 };
 
 static ccl_program g_sort_program = { "clo_sort (precompiled sm_100a)", nullptr, std::string(), nullptr, {} };
@@ -549,6 +550,8 @@ extern "C" void clo_sort_destroy(CloSort* sorter) {
 		clo_radix_state_free(sorter->rs);
 		clo_bitonic_state_free(sorter->bs);
 		clo_jit_sort_free(sorter->jit);
+		sorter->host_in.release();
+		sorter->host_out.release();
 	}
 	ccl_context_unref(sorter->ctx);
 	delete sorter;
@@ -560,73 +563,57 @@ extern "C" CCLEvent* clo_sort_with_device_data(CloSort* sorter, CCLQueue* cq_exe
 	return sorter->impl_def.sort_with_device_data(sorter, cq_exec, cq_comm, data_in, data_out, numel, lws_max, err);
 }
 
-/* clo_sort_abstract.c:296-418 */
+/* Host data in, sorted host data out (the contract of clo_sort_abstract.c:296-418: blocks until
+ * data_out is complete).  The device staging lives in the sorter and only grows -- no
+ * cudaMalloc / cudaFree of gigabytes per call -- and when one queue does everything the copy in,
+ * the sort and the copy out are simply stream ordered: the host blocks once, at the end. */
 extern "C" cl_bool clo_sort_with_host_data(CloSort* sorter, CCLQueue* cq_exec, CCLQueue* cq_comm,
 		void* data_in, void* data_out, size_t numel, size_t lws_max, GError** err) {
 	if (!sorter || (err && *err)) return CL_FALSE;
-	cl_bool status = CL_FALSE;
-	CCLBuffer* in_dev = NULL;
-	CCLBuffer* aux_dev = NULL;
-	CCLBuffer* out_dev = NULL;
-	CCLBuffer* read_dev = NULL;
-	CCLQueue* intern_queue = NULL;
-	CCLEvent* evt = NULL;
+	if (numel && (!data_in || !data_out)) { g_set_error(err, CLO_ERROR, CLO_ERROR_ARGS, "sort: NULL host pointer"); return CL_FALSE; }
+	const size_t bytes = numel * clo_type_sizeof(sorter->elem_type);
+	CCLQueue* own_queue = NULL;
+	if (!cq_exec) {
+		own_queue = ccl_queue_new(sorter->ctx, NULL, 0, err);
+		if (!own_queue) return CL_FALSE;
+		cq_exec = own_queue;
+	}
+	if (!cq_comm) cq_comm = cq_exec;
+	const bool one_queue = cq_comm == cq_exec;
+	cl_bool ok = CL_FALSE;
+	CCLBuffer *in_dev = NULL, *out_dev = NULL;
 	CCLEventWaitList ewl = NULL;
-	GError* ierr = NULL;
-	const size_t data_size = numel * clo_type_sizeof(sorter->elem_type);
-
-	if (cq_exec == NULL) {
-		CCLDevice* dev = ccl_context_get_device(sorter->ctx, 0, &ierr);
-		if (ierr) goto error_handler;
-		intern_queue = ccl_queue_new(sorter->ctx, dev, 0, &ierr);
-		if (ierr) goto error_handler;
-		cq_exec = intern_queue;
+	{
+		CloDeviceGuard g(sorter->ctx->dev.ordinal);
+		const bool two = !sorter->impl_def.in_place;
+		if (clo_cuda_failed(sorter->host_in.reserve(bytes ? bytes : 1), err, "sort staging") ||
+				(two && clo_cuda_failed(sorter->host_out.reserve(bytes ? bytes : 1), err, "sort staging"))) goto done;
+		in_dev = ccl_buffer_new_wrap(sorter->ctx, sorter->host_in.ptr, bytes, err);
+		if (in_dev && two) out_dev = ccl_buffer_new_wrap(sorter->ctx, sorter->host_out.ptr, bytes, err);
+		if (!in_dev || (two && !out_dev)) goto done;
+		CCLEvent* evt = ccl_buffer_enqueue_write(in_dev, cq_comm, CL_FALSE, 0, bytes, data_in, NULL, err);
+		if (!evt) goto done;
+		/* a separate copy queue must have delivered the data; one queue is already ordered */
+		if (!one_queue && !ccl_queue_finish(cq_comm, err)) goto done;
+		evt = sorter->impl_def.sort_with_device_data(sorter, cq_exec, cq_comm, in_dev, out_dev, numel, lws_max, err);
+		if (!evt && numel) goto done;
+		evt = ccl_buffer_enqueue_read(two ? out_dev : in_dev, cq_comm, CL_FALSE, 0, bytes, data_out,
+			(!one_queue && evt) ? ccl_ewl(&ewl, evt, NULL) : NULL, err);
+		if (!evt) goto done;
+		if (!ccl_queue_finish(cq_comm, err)) goto done;                 /* the one blocking point */
+		if (!one_queue && !ccl_queue_finish(cq_exec, err)) goto done;
+		if (clo_radix_status(sorter->rs, cq_exec->stream) != 0) {
+			g_set_error(err, CLO_ERROR, CLO_ERROR_LIBRARY, "radix look-back timed out (device status flag set)");
+			goto done;
+		}
+		ok = CL_TRUE;
 	}
-	if (cq_comm == NULL) cq_comm = cq_exec;
-
-	in_dev = ccl_buffer_new(sorter->ctx, CL_MEM_READ_WRITE, data_size, NULL, &ierr);
-	if (ierr) goto error_handler;
-	if (!sorter->impl_def.in_place) {
-		aux_dev = ccl_buffer_new(sorter->ctx, CL_MEM_READ_WRITE, data_size, NULL, &ierr);
-		if (ierr) goto error_handler;
-		out_dev = aux_dev;
-		read_dev = aux_dev;
-	} else {
-		read_dev = in_dev;
-	}
-
-	evt = ccl_buffer_enqueue_write(in_dev, cq_comm, CL_FALSE, 0, data_size, data_in, NULL, &ierr);
-	if (ierr) goto error_handler;
-	ccl_event_set_name(evt, "write_sort");
-	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
-	if (ierr) goto error_handler;
-
-	evt = sorter->impl_def.sort_with_device_data(sorter, cq_exec, cq_comm, in_dev, out_dev, numel, lws_max, &ierr);
-	if (ierr) goto error_handler;
-
-	evt = ccl_buffer_enqueue_read(read_dev, cq_comm, CL_FALSE, 0, data_size, data_out, ccl_ewl(&ewl, evt, NULL), &ierr);
-	if (ierr) goto error_handler;
-	ccl_event_set_name(evt, "read_sort");
-	ccl_event_wait(ccl_ewl(&ewl, evt, NULL), &ierr);
-	if (ierr) goto error_handler;
-
-	if (clo_radix_status(sorter->rs, cq_exec->stream) != 0) {
-		g_set_error(&ierr, CLO_ERROR, CLO_ERROR_LIBRARY, "radix look-back timed out (device status flag set)");
-		goto error_handler;
-	}
-	status = CL_TRUE;
-	goto finish;
-
-error_handler:
-	g_propagate_error(err, ierr);
-	status = CL_FALSE;
-
-finish:
+done:
 	ccl_event_wait_list_clear(&ewl);
 	if (in_dev) ccl_buffer_destroy(in_dev);
-	if (aux_dev) ccl_buffer_destroy(aux_dev);
-	if (intern_queue) ccl_queue_destroy(intern_queue);
-	return status;
+	if (out_dev) ccl_buffer_destroy(out_dev);
+	if (own_queue) ccl_queue_destroy(own_queue);
+	return ok;
 }
 
 extern "C" CCLContext* clo_sort_get_context(CloSort* s) { return s ? s->ctx : NULL; }
