@@ -114,7 +114,9 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     log2n = 24
     value, ms = cpu_sort_gkeys(log2n, max(1, args.steps), min(args.warmup, 1), threads)
-    sample = "2^%d uint32 keys per step (bounded sample of the 2^28 workload), oracle port of satradix radix=16, OpenMP" % log2n
+    sample = ("2^%d uint32 keys per step (a bounded sample of the 2^28 workload: NOT the same size as the GPU arm), oracle port of "
+              "satradix radix=16 -- 8 passes of tile sort + histogram + scan + scatter, the tile sort done as a counting sort "
+              "instead of the reference's 1-bit-split scan rounds (same result, cheaper on a CPU) -- OpenMP on all host cores" % log2n)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
