@@ -663,6 +663,18 @@ def run_ours(args):
             "repaired_tiles": int(dbg[1]), "lookback_timeout": int(dbg[0]),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "secondary": secondary,
         }
+        # the vendor library on the same kind of box, measured once by tools/cub_yardstick.cu (never
+        # linked into the product); context for the absolute numbers, not part of the metric
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_cub_yardstick.jsonl")) as f:
+                ys = [json.loads(x) for x in f if x.strip()]
+            out["yardstick"] = {"source": "profiles/r2_cub_yardstick.jsonl (tools/cub_yardstick.cu, one B200, recorded; not run here)",
+                                "cub_sort_keys_2p28_u32_gkeys_s": next(y["gkeys_s"] for y in ys if "SortKeys" in y["yardstick"]),
+                                "cub_sort_pairs_u64_u32_gpairs_s": next(y["gpairs_s"] for y in ys if "SortPairs" in y["yardstick"]),
+                                "cub_exclusive_sum_2p30_u32_gbs": next(y["gbs"] for y in ys if "ExclusiveSum" in y["yardstick"] and y["dtype"] == "u32"),
+                                "cub_exclusive_sum_2p30_f32_gbs": next(y["gbs"] for y in ys if "ExclusiveSum" in y["yardstick"] and y["dtype"] == "f32")}
+        except Exception:
+            pass
         if distributed:
             out["phases_ms_rank0"] = {k: round(v, 3) for k, v in phases.items()}
             sc = phases.get("scatter to peers")
