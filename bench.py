@@ -223,6 +223,30 @@ def secondary_single(torch, clo, ctx, queue, peak, sorter, log2n):
         ok = bool(torch.equal(o.to(torch.int64) & m, ref & m))
         sec[name] = {"n": ns, "ms": ms, "gbs": bpe * ns / ms / 1e6, "frac": bpe * ns / ms / 1e6 / peak, "bytes_per_elem": bpe, "bit_exact": ok}
         bi.destroy(); bo.destroy(); sc.destroy(); del o, ref
+    # -- C4 end to end: clo_scan_with_host_data on pinned host buffers, 2^28 elements (1 GiB each way).
+    #    The call pipelines 2^24-element chunks (copy in | scan with carry | copy out), so both directions
+    #    of the host link are busy at once; beside it the same bytes as plain sequential pinned copies.
+    ne = 1 << 28
+    h_x = torch.empty(ne, dtype=torch.int32).pin_memory(); h_x.copy_(x[:ne].cpu())
+    h_o = torch.empty(ne, dtype=torch.int32).pin_memory()
+    d_tmp = torch.empty(ne, dtype=torch.int32, device="cuda")
+    sc = clo.CloScan("blelloch", ctx, clo.UINT, clo.UINT)
+    sc.with_host_pointers(h_x.data_ptr(), h_o.data_ptr(), ne, queue)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        sc.with_host_pointers(h_x.data_ptr(), h_o.data_ptr(), ne, queue)
+    dt = (time.perf_counter() - t0) / 5
+    ref = (torch.cumsum(x[:ne].to(torch.int64), 0) - x[:ne]) & 0xFFFFFFFF
+    ok = bool(torch.equal(h_o.to(torch.int64).cuda() & 0xFFFFFFFF, ref))
+    d_tmp.copy_(h_x, non_blocking=True); h_o.copy_(d_tmp, non_blocking=True); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        d_tmp.copy_(h_x, non_blocking=True); h_o.copy_(d_tmp, non_blocking=True); torch.cuda.synchronize()
+    fl = (time.perf_counter() - t0) / 5
+    sec["scan_u32_u32_e2e"] = {"n": ne, "ms": dt * 1e3, "gbs": 8.0 * ne / dt / 1e9, "h2d_bytes": 4 * ne, "d2h_bytes": 4 * ne,
+                               "sequential_copies_ms": fl * 1e3, "speedup_vs_sequential_copies": fl / dt, "bit_exact": ok,
+                               "api": "clo_scan_with_host_data (pinned host buffers; chunks of 2^24 elements pipelined: H2D | scan | D2H)"}
+    sc.destroy(); del h_x, h_o, d_tmp, ref
     del x
     torch.cuda.empty_cache()
     xf = torch.rand(ns, dtype=torch.float32, device="cuda", generator=g)

@@ -435,6 +435,15 @@ class CloScan:
             raise CloError(CLO_ERROR_LIBRARY, "clo_scan_with_host_data failed")
         return out
 
+    def with_host_pointers(self, in_ptr, out_ptr, numel, queue=None, lws_max=0):
+        """clo_scan_with_host_data on raw host addresses (e.g. pinned torch tensors)."""
+        e = _Err()
+        ok = lib().clo_scan_with_host_data(self.h, queue.h if queue else None, None, ctypes.c_void_p(in_ptr),
+                                           ctypes.c_void_p(out_ptr), numel, lws_max, e.ref())
+        e.check()
+        if not ok:
+            raise CloError(CLO_ERROR_LIBRARY, "clo_scan_with_host_data failed")
+
     def with_device_data(self, queue, data_in, data_out, numel, lws_max=0, carry_in=None):
         e = _Err()
         if carry_in is None:

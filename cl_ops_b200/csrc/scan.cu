@@ -584,8 +584,21 @@ cudaError_t launch_reduce(ScanState& st, const void* in, void* total_out, size_t
 	return cudaGetLastError();
 }
 
+/* carry of the NEXT chunk of a chunked scan: exclusive sum of the chunk's last element + that element */
+template <typename ElemT, typename SumT>
+__global__ void clo_scan_next_carry(const ElemT* __restrict__ in, const SumT* __restrict__ out, size_t n, SumT* __restrict__ carry) {
+	if (threadIdx.x == 0 && blockIdx.x == 0 && n) *carry = static_cast<SumT>(out[n - 1] + static_cast<SumT>(in[n - 1]));
+}
+template <typename ElemT, typename SumT>
+cudaError_t launch_next_carry(const void* in, const void* out, size_t n, void* carry, cudaStream_t stream) {
+	clo_scan_next_carry<ElemT, SumT><<<1, 32, 0, stream>>>((const ElemT*) in, (const SumT*) out, n, (SumT*) carry);
+	CLO_COUNT_LAUNCH(1);
+	return cudaGetLastError();
+}
+
 typedef cudaError_t (*ScanFn)(ScanState&, const void*, void*, size_t, const void*, int, cudaStream_t);
 typedef cudaError_t (*ReduceFn)(ScanState&, const void*, void*, size_t, int, cudaStream_t);
+typedef cudaError_t (*CarryFn)(const void*, const void*, size_t, void*, cudaStream_t);
 
 /* CloType -> C++ type (half is not an arithmetic type in OpenCL C without
  * cl_khr_fp16; unsupported here as well) */
@@ -604,6 +617,7 @@ template <> struct CT<CLO_DOUBLE> { typedef double type; };
 template <int E, int S> struct Entry {
 	static ScanFn scan() { return &launch_scan<typename CT<E>::type, typename CT<S>::type>; }
 	static ReduceFn reduce() { return &launch_reduce<typename CT<E>::type, typename CT<S>::type>; }
+	static CarryFn carry() { return &launch_next_carry<typename CT<E>::type, typename CT<S>::type>; }
 };
 
 #define CLO_TYPE_CASES(M) \
@@ -637,6 +651,24 @@ ScanFn find_scan(int e, int s) {
 	}
 }
 
+template <int E> CarryFn carry_for_sum(int s) {
+	switch (s) {
+#define CLO_M(S) case S: return Entry<E, S>::carry();
+	CLO_TYPE_CASES(CLO_M)
+#undef CLO_M
+	default: return nullptr;
+	}
+}
+
+CarryFn find_carry(int e, int s) {
+	switch (e) {
+#define CLO_M(E) case E: return carry_for_sum<E>(s);
+	CLO_TYPE_CASES(CLO_M)
+#undef CLO_M
+	default: return nullptr;
+	}
+}
+
 ReduceFn find_reduce(int e, int s) {
 	switch (e) {
 #define CLO_M(E) case E: return reduce_for_sum<E>(s);
@@ -662,6 +694,10 @@ struct clo_scan {
 	ScanFn fn;
 	ReduceFn rfn;
 	CloScratch host_in, host_out;   /* device staging of clo_scan_with_host_data, kept between calls */
+	CarryFn cfn;
+	cudaStream_t s_in = nullptr, s_out = nullptr;      /* copy streams of the chunked host path */
+	cudaEvent_t ev_in[4] = {}, ev_sc[4] = {};
+	void* d_chunk_carry = nullptr;
 };
 
 static ccl_program g_scan_program = { "clo_scan (precompiled sm_100a)", nullptr, std::string(), nullptr, {} };
@@ -782,7 +818,7 @@ extern "C" CloScan* clo_scan_new(const char* type, const char* options, CCLConte
 	s->prg = &g_scan_program;
 	s->elem_type = elem_type; s->sum_type = sum_type;
 	s->data = NULL;
-	s->fn = fn; s->rfn = find_reduce((int) elem_type, (int) sum_type);
+	s->fn = fn; s->rfn = find_reduce((int) elem_type, (int) sum_type); s->cfn = find_carry((int) elem_type, (int) sum_type);
 	{ const char* c = getenv("CLO_SCAN_CFG"); s->st.cfg = (c && *c) ? atoi(c) : 0; }
 	{ const char* c = getenv("CLO_SCAN_KERNEL"); s->st.use_pp = (c && strcmp(c, "classic") == 0) ? 0 : 1;
 	  s->st.use_tma = (c && (strcmp(c, "pp") == 0 || strcmp(c, "classic") == 0)) ? 0 : 1;
@@ -812,6 +848,10 @@ extern "C" void clo_scan_destroy(CloScan* scan) {
 		scan->st.pp.release();
 		scan->host_in.release();
 		scan->host_out.release();
+		if (scan->s_in) cudaStreamDestroy(scan->s_in);
+		if (scan->s_out) cudaStreamDestroy(scan->s_out);
+		for (int i = 0; i < 4; ++i) { if (scan->ev_in[i]) cudaEventDestroy(scan->ev_in[i]); if (scan->ev_sc[i]) cudaEventDestroy(scan->ev_sc[i]); }
+		if (scan->d_chunk_carry) cudaFree(scan->d_chunk_carry);
 	}
 	ccl_context_unref(scan->ctx);
 	delete scan;
@@ -874,6 +914,55 @@ extern "C" cl_bool clo_scan_with_host_data(CloScan* scanner, CCLQueue* cq_exec, 
 		in_dev = ccl_buffer_new_wrap(scanner->ctx, scanner->host_in.ptr, in_size, err);
 		if (in_dev) out_dev = ccl_buffer_new_wrap(scanner->ctx, scanner->host_out.ptr, out_size, err);
 		if (!in_dev || !out_dev) goto done;
+		/* Large inputs go through in CHUNKS: while chunk i is scanned (carry-in = everything before
+		 * it, kept on the device), chunk i+1 is on its way in and chunk i-1 on its way out -- the two
+		 * directions of the host link run at the same time, so the call costs about ONE transfer of
+		 * the larger side instead of copy in + scan + copy out.  CLO_SCAN_HOST_CHUNK (elements) tunes
+		 * or disables (0) it. */
+		const char* chunk_e = getenv("CLO_SCAN_HOST_CHUNK");
+		const size_t chunk = (chunk_e && *chunk_e) ? (size_t) atoll(chunk_e) : ((size_t) 1 << 24);
+		if (one_queue && chunk && numel >= 2 * chunk && scanner->cfn) {
+			const size_t es = clo_type_sizeof(scanner->elem_type), ss = clo_type_sizeof(scanner->sum_type);
+			bool ready = true;
+			if (!scanner->s_in) {
+				ready = cudaStreamCreateWithFlags(&scanner->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+					cudaStreamCreateWithFlags(&scanner->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+					cudaMalloc(&scanner->d_chunk_carry, 16) == cudaSuccess;
+				for (int i = 0; ready && i < 4; ++i)
+					ready = cudaEventCreateWithFlags(&scanner->ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+						cudaEventCreateWithFlags(&scanner->ev_sc[i], cudaEventDisableTiming) == cudaSuccess;
+			}
+			if (clo_cuda_failed(ready ? cudaSuccess : cudaErrorMemoryAllocation, err, "scan host pipeline")) goto done;
+			cudaStream_t se = cq_exec->stream;
+			const int sms = clo_sm_count(cq_exec->ctx->dev.ordinal);
+			/* the copy streams start after whatever the caller already queued */
+			cudaEventRecord(scanner->ev_sc[3], se);
+			cudaStreamWaitEvent(scanner->s_in, scanner->ev_sc[3], 0);
+			cudaStreamWaitEvent(scanner->s_out, scanner->ev_sc[3], 0);
+			cudaError_t rc = cudaSuccess;
+			size_t idx = 0;
+			for (size_t off = 0; off < numel && rc == cudaSuccess; off += chunk, ++idx) {
+				const size_t cnt = numel - off < chunk ? numel - off : chunk;
+				const int k = (int) (idx % 3);
+				const char* din = (const char*) scanner->host_in.ptr + off * es;
+				char* dout = (char*) scanner->host_out.ptr + off * ss;
+				rc = cudaMemcpyAsync((void*) din, (const char*) data_in + off * es, cnt * es, cudaMemcpyHostToDevice, scanner->s_in);
+				if (rc == cudaSuccess) rc = cudaEventRecord(scanner->ev_in[k], scanner->s_in);
+				if (rc == cudaSuccess) rc = cudaStreamWaitEvent(se, scanner->ev_in[k], 0);
+				if (rc == cudaSuccess) rc = scanner->fn(scanner->st, din, dout, cnt, off ? scanner->d_chunk_carry : NULL, sms, se);
+				if (rc == cudaSuccess && off + cnt < numel) rc = scanner->cfn(din, dout, cnt, scanner->d_chunk_carry, se);
+				if (rc == cudaSuccess) rc = cudaEventRecord(scanner->ev_sc[k], se);
+				if (rc == cudaSuccess) rc = cudaStreamWaitEvent(scanner->s_out, scanner->ev_sc[k], 0);
+				if (rc == cudaSuccess) rc = cudaMemcpyAsync((char*) data_out + off * ss, dout, cnt * ss, cudaMemcpyDeviceToHost, scanner->s_out);
+				/* an event slot is reused three chunks later: its waiters have been queued long before */
+			}
+			if (rc == cudaSuccess) rc = cudaStreamSynchronize(scanner->s_out);       /* the one blocking point */
+			if (rc == cudaSuccess) rc = cudaStreamSynchronize(se);
+			if (clo_cuda_failed(rc, err, "scan host pipeline")) goto done;
+			if (scan_check_error_flag(scanner, se, err)) goto done;
+			ok = CL_TRUE;
+			goto done;
+		}
 		CCLEvent* evt = ccl_buffer_enqueue_write(in_dev, cq_comm, CL_FALSE, 0, in_size, data_in, NULL, err);
 		if (!evt) goto done;
 		if (!one_queue && !ccl_queue_finish(cq_comm, err)) goto done;

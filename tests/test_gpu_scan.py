@@ -183,6 +183,38 @@ def test_scan_copy_engine_kernel(clo, ctx, queue, et, n, monkeypatch):
     s.destroy()
 
 
+@pytest.mark.parametrize("et,st", [(oracle.UINT, oracle.UINT), (oracle.UINT, oracle.ULONG), (oracle.INT, oracle.LONG),
+                                   (oracle.FLOAT, oracle.FLOAT), (oracle.UCHAR, oracle.UINT)])
+@pytest.mark.parametrize("chunk,n", [("100000", 1234567), ("65536", 65536 * 5), (None, (1 << 25) + 77)])
+def test_scan_host_data_is_pipelined_in_chunks(clo, ctx, queue, et, st, chunk, n, monkeypatch):
+    """clo_scan_with_host_data on large inputs: chunks go in, are scanned with the carry of everything
+    before them and come out while the next chunk is already on its way (both directions of the host
+    link busy).  Same bits as the oracle for integers (wrap-around kept across chunk borders)."""
+    if chunk is not None:
+        monkeypatch.setenv("CLO_SCAN_HOST_CHUNK", chunk)
+    rng = np.random.default_rng(n % 977 + et + st)
+    dt = oracle.NP_TYPES[et]
+    if np.issubdtype(dt, np.integer):
+        info = np.iinfo(dt)
+        a = rng.integers(info.min, info.max, size=n, dtype=dt, endpoint=True)
+    else:
+        a = rng.random(n).astype(dt)
+    s = clo.CloScan("blelloch", ctx, et, st)
+    for rep in range(2):
+        got = s.with_host_data(a, queue)
+        if np.issubdtype(dt, np.integer):
+            assert np.array_equal(got, oracle.scan(a, et, st))
+        else:
+            ref = np.cumsum(a.astype(np.float64)) - a
+            assert np.all(np.abs(got - ref) <= 1e-5 * np.abs(ref) + 1e-3)
+    # and with the pipeline off: the same result
+    monkeypatch.setenv("CLO_SCAN_HOST_CHUNK", "0")
+    got0 = s.with_host_data(a, queue)
+    if np.issubdtype(dt, np.integer):
+        assert np.array_equal(got0, got)
+    s.destroy()
+
+
 def test_scan_errors(clo, ctx):
     with pytest.raises(clo.CloError) as ei:
         clo.CloScan("nosuchscan", ctx, oracle.UINT, oracle.UINT)
