@@ -322,6 +322,7 @@ struct CloBitonicState {
 	int max_log_tile = 13;   /* cap of the shared-memory tile, log2 elements (abitonic option maxsfs) */
 };
 
+#ifndef CLO_BITONIC_ONLY
 CloBitonicState* clo_bitonic_state_new() { return new CloBitonicState(); }
 
 void clo_bitonic_state_free(CloBitonicState* st) {
@@ -336,6 +337,8 @@ void clo_bitonic_set_fusion(CloBitonicState* st, int max_private_steps, int max_
 	st->kmax = max_private_steps < 1 ? 1 : (max_private_steps > 5 ? 5 : max_private_steps);
 	st->max_log_tile = max_local_steps < 5 ? 5 : (max_local_steps > 13 ? 13 : max_local_steps);
 }
+
+#endif
 
 namespace {
 /* power-of-two n: the whole network as one cooperative launch; false when that is not possible */
@@ -417,14 +420,39 @@ cudaError_t bitonic_typed(CloBitonicState* st, const CloKeySpec& ks, void* data,
 }
 }
 
+/* The fused kernel is heavy to compile (k <= 5 unrolled register networks per element width and
+ * comparator form: 7 minutes in one translation unit), so the Makefile compiles this file once
+ * per element width with -DCLO_BITONIC_ONLY=<bytes>, in parallel; each of those objects holds one
+ * clo_bitonic_typed_<bytes>, and the plain object the entry points that dispatch to them. */
+#ifdef CLO_BITONIC_ONLY
+#define CLO_BT_CAT2(a, b) a##b
+#define CLO_BT_CAT(a, b) CLO_BT_CAT2(a, b)
+#if CLO_BITONIC_ONLY == 1
+typedef unsigned char CloBitonicOnlyT;
+#elif CLO_BITONIC_ONLY == 2
+typedef unsigned short CloBitonicOnlyT;
+#elif CLO_BITONIC_ONLY == 4
+typedef u32 CloBitonicOnlyT;
+#else
+typedef u64 CloBitonicOnlyT;
+#endif
+cudaError_t CLO_BT_CAT(clo_bitonic_typed_, CLO_BITONIC_ONLY)(CloBitonicState* st, const CloKeySpec& ks, void* data, size_t n, cudaStream_t stream) {
+	return bitonic_typed<CloBitonicOnlyT>(st, ks, data, n, stream);
+}
+#else
+cudaError_t clo_bitonic_typed_1(CloBitonicState* st, const CloKeySpec& ks, void* data, size_t n, cudaStream_t stream);
+cudaError_t clo_bitonic_typed_2(CloBitonicState* st, const CloKeySpec& ks, void* data, size_t n, cudaStream_t stream);
+cudaError_t clo_bitonic_typed_4(CloBitonicState* st, const CloKeySpec& ks, void* data, size_t n, cudaStream_t stream);
+cudaError_t clo_bitonic_typed_8(CloBitonicState* st, const CloKeySpec& ks, void* data, size_t n, cudaStream_t stream);
+
 cudaError_t clo_bitonic_sort(CloBitonicState* st, size_t elem_size, const CloKeySpec& ks,
 		void* data, size_t n, cudaStream_t stream) {
 	if (n < 2) return cudaSuccess;
 	switch (elem_size) {
-	case 1: return bitonic_typed<unsigned char>(st, ks, data, n, stream);
-	case 2: return bitonic_typed<unsigned short>(st, ks, data, n, stream);
-	case 4: return bitonic_typed<u32>(st, ks, data, n, stream);
-	case 8: return bitonic_typed<u64>(st, ks, data, n, stream);
+	case 1: return clo_bitonic_typed_1(st, ks, data, n, stream);
+	case 2: return clo_bitonic_typed_2(st, ks, data, n, stream);
+	case 4: return clo_bitonic_typed_4(st, ks, data, n, stream);
+	case 8: return clo_bitonic_typed_8(st, ks, data, n, stream);
 	default: return cudaErrorInvalidValue;
 	}
 }
@@ -443,3 +471,4 @@ cudaError_t clo_gselect_sort(size_t elem_size, const CloKeySpec& ks, const void*
 	CLO_COUNT_LAUNCH(1);
 	return cudaGetLastError();
 }
+#endif
