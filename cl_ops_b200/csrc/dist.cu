@@ -166,7 +166,7 @@ __global__ void clo_dist_wait(const u64* __restrict__ ctl, u32 world, u32 flag, 
 		const volatile u64* f = ctl + CTL_FLAGS + (size_t) flag * DIST_MAX_WORLD + threadIdx.x;
 		const long long t0 = clock64();
 		while (*f < epoch) {
-			if (clock64() - t0 > 8000000000ll) { atomicExch(err, 1); break; }      /* ~4 s: a peer never arrived */
+			if (clock64() - t0 > 60000000000ll) { atomicExch(err, 1); break; }     /* ~30 s: a peer never arrived (ranks may be seconds apart on a first call) */
 			__nanosleep(200);
 		}
 	}
