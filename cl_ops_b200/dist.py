@@ -97,8 +97,19 @@ class GpuOps:
         (what the gloo tests exercise on the CPU)."""
         impl = impl or os.environ.get("CLO_DIST_IMPL", "c")
         if impl == "c":
-            self.cd = self.clo.CloDist(self.ctx, group)
-            self.cd.sort_setup(self.key_type, capacity, with_payload)
+            try:
+                self.cd = self.clo.CloDist(self.ctx, group)
+                self.cd.sort_setup(self.key_type, capacity, with_payload)
+            except self.clo.CloError as e:
+                # the library agrees on set-up failures across ranks (every rank gets the error), so
+                # every rank takes the module's own driver below; say so, this is not the product path
+                import sys
+                print("cl_ops_b200.dist: clo_dist set-up failed (%s); using the Python driver" % e.message, file=sys.stderr)
+                if getattr(self, "cd", None) is not None:
+                    self.cd.destroy()
+                self.cd = None
+                impl = "py"
+        if impl == "c":
             dev = torch.device("cuda", torch.cuda.current_device())
             self.cd_with_payload = with_payload
             self.cd_capacity = capacity
