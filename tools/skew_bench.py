@@ -46,6 +46,12 @@ for name, t in cases.items():
     torch.cuda.synchronize()
     tm = [round(x, 3) for x in s.get_timing()]
     s.set_timing(False)
-    print(json.dumps({"keys": name, "ms": round(ms, 3), "gkeys": round(n / ms / 1e6, 1), "sorted": ok, "repaired": d[1], "timeout": d[0],
-                      "kernel_ms": tm}), flush=True)
+    rec = {"keys": name, "ms": round(ms, 3), "gkeys": round(n / ms / 1e6, 1), "sorted": ok, "repaired": d[1], "timeout": d[0],
+           "kernel_ms": tm}
+    if os.environ.get("CLO_RADIX_PROFILE"):
+        # cycles per phase of worker thread 0, summed over the tiles of the LAST call (radix_v6.cuh mark())
+        names = ["P1 count+loadwait", "B1 wait", "P2 digits", "B2 wait", "P5 write-out", "B3 wait", "P3 place+P4 load"]
+        tiles = 4 * ((n + 8191) // 8192)
+        rec["cycles_per_tile"] = {k: round(v / tiles, 1) for k, v in zip(names, d[2:9])}
+    print(json.dumps(rec), flush=True)
     bi.destroy(); del uo
