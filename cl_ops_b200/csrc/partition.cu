@@ -104,6 +104,26 @@ __device__ __forceinline__ u32 pt_bucket_lane(ElemT k, u64 g, const PtSplitters<
 	return b;
 }
 
+/* the same bucket, with the sorted splitter keys in SHARED memory: three broadcast-friendly loads
+ * replace the register select chains of pt_pick (which made the 8-way count ALU bound) */
+template <typename ElemT, int NS>
+__device__ __forceinline__ u32 pt_bucket_smem(ElemT k, u64 g, const ElemT* __restrict__ s_sk, const PtSplitters<ElemT, NS>& sp) {
+	u32 b = 0;
+	bool tie = false;
+#pragma unroll
+	for (int step = (NS + 1) / 2; step >= 1; step >>= 1) {
+		const ElemT pivot = s_sk[b + (u32) step - 1u];
+		tie |= pivot == k;
+		b += pivot < k ? (u32) step : 0u;
+	}
+	if (tie) {
+		b = 0;
+#pragma unroll
+		for (int s = 0; s < NS; ++s) b += (sp.key[s] < k || (sp.key[s] == k && sp.idx[s] <= g)) ? 1u : 0u;
+	}
+	return b;
+}
+
 /* Bucket sizes per scatter chunk (chunk w = [w * chunk, min(n, (w + 1) * chunk)) is what warp w of
  * the scatter kernel will move).  Round 2: counting streams through the keys like any grid-stride
  * kernel -- sub-blocks of PT_SUB keys, handed to the warps round-robin, so the chip reads one
@@ -123,6 +143,12 @@ clo_partition_count(const ElemT* __restrict__ in, size_t n, size_t chunk, u32 to
 	constexpr int VPL = PT_SUB / 32 / EPV;              /* 16-byte vectors per lane and sub-block */
 	PtSplitters<ElemT, NS> sp;
 	pt_load_splitters<ElemT, NS>(sp, sk, si, nsplit, gidx0);
+	constexpr bool SMEM_SEARCH = NS >= 3;
+	__shared__ ElemT s_sk[NS + 1];
+	if (SMEM_SEARCH) {
+		if (threadIdx.x < NS) s_sk[threadIdx.x] = threadIdx.x < nsplit ? sk[threadIdx.x] : (ElemT) ~(ElemT) 0;
+		__syncthreads();
+	}
 	const int lane = threadIdx.x & 31;
 	const size_t gw = (size_t) blockIdx.x * PT_WARPS + (threadIdx.x >> 5);
 	const size_t nwarps = (size_t) gridDim.x * PT_WARPS;
@@ -134,7 +160,7 @@ clo_partition_count(const ElemT* __restrict__ in, size_t n, size_t chunk, u32 to
 		const bool full = vec_ok && lo + PT_SUB <= n;
 		u64 acc0 = 0, acc1 = 0;
 		auto count_one = [&](ElemT k, size_t i) {
-			const u32 bkt = pt_bucket_lane<ElemT, NS>(k, sp.gidx0 + i, sp);
+			const u32 bkt = SMEM_SEARCH ? pt_bucket_smem<ElemT, NS>(k, sp.gidx0 + i, s_sk, sp) : pt_bucket_lane<ElemT, NS>(k, sp.gidx0 + i, sp);
 			const u64 inc = 1ull << ((bkt & 7u) << 3);
 			if (NB <= 8) acc0 += inc;
 			else { acc0 += bkt < 8u ? inc : 0ull; acc1 += bkt < 8u ? 0ull : inc; }
@@ -231,6 +257,15 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 	if (ok && *ok == 0) return;
 	PtSplitters<ElemT, NS> sp;
 	pt_load_splitters<ElemT, NS>(sp, sk, si, nsplit, gidx0);
+	/* splitter keys also in shared memory: the bucket search is three loads instead of select chains */
+	constexpr size_t RING_BYTES = (size_t) SW * NB * 64 * (sizeof(ElemT) + (HAS_VAL ? 4 : 0));
+	constexpr bool SMEM_SEARCH = NS >= 3 && RING_BYTES + (NS + 1) * sizeof(ElemT) <= 48 * 1024;
+	__shared__ ElemT s_sk[SMEM_SEARCH ? NS + 1 : 1];
+	if (SMEM_SEARCH) {
+		/* written by every warp with the same values: no CTA barrier (some warps have returned) */
+		if (lane < NS) s_sk[lane] = (u32) lane < nsplit ? sk[lane] : (ElemT) ~(ElemT) 0;
+		__syncwarp();
+	}
 	ElemT* kp = nullptr;          /* next element of bucket `lane` to be written */
 	u32* vp = nullptr;
 	u32 head = 0, cnt = 0;        /* ring of bucket `lane`: first pending slot, pending elements */
@@ -267,7 +302,20 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 		for (int u = 0; u < PT_U; ++u) {
 			const size_t i = base + u * 32 + lane;
 			const bool valid = i < hi;
-			u32 b = pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp);
+			u32 b;
+			if (SMEM_SEARCH) {
+				b = 0;
+				bool tie = false;
+#pragma unroll
+				for (int step = (NS + 1) / 2; step >= 1; step >>= 1) {
+					const ElemT pivot = s_sk[b + (u32) step - 1u];
+					tie |= pivot == k[u];
+					b += pivot < k[u] ? (u32) step : 0u;
+				}
+				if (__any_sync(0xffffffffu, tie)) b = pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp);     /* rare: the exact rule, whole warp */
+			} else {
+				b = pt_bucket<ElemT, NS>(k[u], sp.gidx0 + i, sp);
+			}
 			if (!valid) b = 0xffffffffu;
 			/* lanes of my bucket / lanes of bucket `lane`: one ballot per bucket BIT */
 			u32 mine = __ballot_sync(0xffffffffu, valid), forq = mine;
