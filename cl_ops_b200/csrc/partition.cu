@@ -274,6 +274,7 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 		kp = dests[lane] + slot;
 		if (HAS_VAL) vp = vdests[lane] + slot;
 	}
+	u32 thr = 32u - (u32) ((reinterpret_cast<uintptr_t>(kp) & 127) / sizeof(ElemT));
 	ElemT (*ring)[64] = s_key[warp];
 	const size_t lo = (size_t) w * chunk;
 	const size_t hi = lo + chunk < n ? lo + chunk : n;
@@ -287,21 +288,23 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 			u32* dv = reinterpret_cast<u32*>(__shfl_sync(0xffffffffu, (u64) reinterpret_cast<uintptr_t>(vp), q));
 			if ((u32) lane < f) dv[lane] = s_val[HAS_VAL ? warp : 0][HAS_VAL ? q : 0][HAS_VAL ? ((h + lane) & 63) : 0];
 		}
-		if (lane == q) { head = (head + f) & 63; cnt -= f; kp += f; if (HAS_VAL) vp += f; }
+		if (lane == q) { head = (head + f) & 63; cnt -= f; kp += f; if (HAS_VAL) vp += f; thr = 32u; }
 	};
-	for (size_t base = lo; base < hi; base += 32 * PT_U) {
+	/* one step = PT_U rows of 32 keys; FULL steps (all but the last of the array) skip every bounds check */
+	auto step_rows = [&](size_t base, auto full_tag) {
+		constexpr bool FULL = decltype(full_tag)::value;
 		ElemT k[PT_U];
 		u32 v[HAS_VAL ? PT_U : 1];
 #pragma unroll
 		for (int u = 0; u < PT_U; ++u) {
 			const size_t i = base + u * 32 + lane;
-			k[u] = i < hi ? __ldcs(in + i) : ElemT(0);
-			if (HAS_VAL) v[u] = i < hi ? __ldcs(vin + i) : 0u;
+			k[u] = (FULL || i < hi) ? __ldcs(in + i) : ElemT(0);
+			if (HAS_VAL) v[u] = (FULL || i < hi) ? __ldcs(vin + i) : 0u;
 		}
 #pragma unroll
 		for (int u = 0; u < PT_U; ++u) {
 			const size_t i = base + u * 32 + lane;
-			const bool valid = i < hi;
+			const bool valid = FULL || i < hi;
 			u32 b;
 			if (SMEM_SEARCH) {
 				b = 0;
@@ -318,7 +321,7 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 			}
 			if (!valid) b = 0xffffffffu;
 			/* lanes of my bucket / lanes of bucket `lane`: one ballot per bucket BIT */
-			u32 mine = __ballot_sync(0xffffffffu, valid), forq = mine;
+			u32 mine = FULL ? 0xffffffffu : __ballot_sync(0xffffffffu, valid), forq = mine;
 #pragma unroll
 			for (int j = 0; (1 << j) < NB; ++j) {
 				const u32 bj = __ballot_sync(0xffffffffu, (b >> j) & 1u);
@@ -335,10 +338,9 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 			}
 			cnt += add;
 			__syncwarp();
-			/* buckets that can fill a line up to the next 128-byte boundary */
+			/* buckets that can fill a line up to the next 128-byte boundary (thr: elements up to it;
+			 * a flush always ends on the boundary, so it is 32 from the bucket's first flush on) */
 			for (;;) {
-				const u32 mis = (u32) ((reinterpret_cast<uintptr_t>(kp) & 127) / sizeof(ElemT));
-				const u32 thr = 32u - mis;
 				u32 need = __ballot_sync(0xffffffffu, lane < NB && cnt >= thr);
 				if (!need) break;
 				while (need) {
@@ -349,6 +351,10 @@ clo_partition_scatter(const ElemT* __restrict__ in, const u32* __restrict__ vin,
 				__syncwarp();
 			}
 		}
+	};
+	for (size_t base = lo; base < hi; base += 32 * PT_U) {
+		if (base + 32 * PT_U <= hi) step_rows(base, std::true_type{});
+		else step_rows(base, std::false_type{});
 	}
 	/* drain */
 	for (int q = 0; q < NB; ++q) {
