@@ -101,15 +101,15 @@ clo_radix_histogram(const ElemT* __restrict__ in, size_t n, u64* __restrict__ gh
 	if (vec_ok) {
 		const size_t nvec = n / EPV;
 		size_t i = tid;
-		/* two vectors in flight per thread */
-		for (; i + stride < nvec; i += 2 * stride) {
-			ElemT e0[EPV], e1[EPV];
-			load_vec_cs<ElemT, EPV>(in + i * EPV, e0);
-			load_vec_cs<ElemT, EPV>(in + (i + stride) * EPV, e1);
+		/* four vectors in flight per thread */
+		for (; i + 3 * stride < nvec; i += 4 * stride) {
+			ElemT e[4][EPV];
 #pragma unroll
-			for (int c = 0; c < EPV; ++c) count(e0[c]);
+			for (int u = 0; u < 4; ++u) load_vec_cs<ElemT, EPV>(in + (i + u * stride) * EPV, e[u]);
 #pragma unroll
-			for (int c = 0; c < EPV; ++c) count(e1[c]);
+			for (int u = 0; u < 4; ++u)
+#pragma unroll
+				for (int c = 0; c < EPV; ++c) count(e[u][c]);
 		}
 		for (; i < nvec; i += stride) {
 			ElemT e0[EPV];
