@@ -152,10 +152,36 @@ clo_radix_onesweep_v6(const ElemT* in_arg, ElemT* out_arg,
 	 * the pass reads the current location from the chain word its predecessor wrote, sorts into
 	 * whichever of the two it is not reading, and tells its successor (block 0).  chain_in ==
 	 * NULL: the first pass, or a caller that still moves the keys itself (identity = copy). */
-	const ElemT* __restrict__ in = chain_in ? (const ElemT*) chain_in->cur : in_arg;
-	const u32* __restrict__ vin = chain_in ? (const u32*) chain_in->vcur : vin_arg;
-	ElemT* __restrict__ out = ((const void*) out_arg == (const void*) in && out_alt) ? out_alt : out_arg;
-	u32* __restrict__ vout = ((const void*) out_arg == (const void*) in && out_alt) ? vout_alt : vout_arg;
+	/* For 8-byte keys and for key + payload sorts the four resolved pointers live in SHARED memory,
+	 * not in registers: kernel parameters cost no registers (constant bank), values loaded from the
+	 * chain word do -- eight of them, which at the 64-register cap of this kernel meant more spills
+	 * (pairs u64 + u32: 8.23 -> 7.69 ms per 2^27 with the pointers in shared memory; every use is per
+	 * tile, so a broadcast load each time is free).  The 4-byte keys-only instance is the other way
+	 * round (2.80 vs 2.92 ms per 2^28): it keeps them in registers. */
+	constexpr bool PTRS_IN_SMEM = HAS_VAL || sizeof(ElemT) == 8;
+	__shared__ struct { const ElemT* in; ElemT* out; const u32* vin; u32* vout; } s_p;
+	const ElemT* r_in = nullptr; const u32* r_vin = nullptr; ElemT* r_out = nullptr; u32* r_vout = nullptr;
+	if (PTRS_IN_SMEM) {
+		if (threadIdx.x == 0) {
+			const ElemT* in0 = chain_in ? (const ElemT*) chain_in->cur : in_arg;
+			const bool swap = (const void*) out_arg == (const void*) in0 && out_alt;
+			s_p.in = in0;
+			s_p.vin = chain_in ? (const u32*) chain_in->vcur : vin_arg;
+			s_p.out = swap ? out_alt : out_arg;
+			s_p.vout = swap ? vout_alt : vout_arg;
+		}
+		__syncthreads();
+	} else {
+		r_in = chain_in ? (const ElemT*) chain_in->cur : in_arg;
+		r_vin = chain_in ? (const u32*) chain_in->vcur : vin_arg;
+		const bool swap = (const void*) out_arg == (const void*) r_in && out_alt;
+		r_out = swap ? out_alt : out_arg;
+		r_vout = swap ? vout_alt : vout_arg;
+	}
+	const ElemT* const& in = PTRS_IN_SMEM ? s_p.in : r_in;
+	const u32* const& vin = PTRS_IN_SMEM ? s_p.vin : r_vin;
+	ElemT* const& out = PTRS_IN_SMEM ? s_p.out : r_out;
+	u32* const& vout = PTRS_IN_SMEM ? s_p.vout : r_vout;
 	constexpr int WARPS = THREADS / 32;
 	constexpr int TILE = THREADS * IPT;
 	constexpr u32 NONE = 0xffffffffu;
