@@ -34,16 +34,19 @@ __device__ __forceinline__ void stm_mbar_init(u64* bar, unsigned count) {
 __device__ __forceinline__ void stm_mbar_expect_tx(u64* bar, unsigned bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(stm_smem(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void stm_mbar_wait(u64* bar, unsigned parity) {
-	asm volatile(
-		"{\n"
-		".reg .pred p;\n"
-		"STM_WAIT_%=:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-		"@p bra STM_DONE_%=;\n"
-		"bra STM_WAIT_%=;\n"
-		"STM_DONE_%=:\n"
-		"}\n" :: "r"(stm_smem(bar)), "r"(parity) : "memory");
+/* bounded: a copy that never lands (a bad descriptor, a fault) must not hang the GPU; false = timed out */
+__device__ __forceinline__ bool stm_mbar_wait(u64* bar, unsigned parity) {
+	for (unsigned tries = 0; tries < (1u << 24); ++tries) {
+		unsigned ok;
+		asm volatile(
+			"{\n"
+			".reg .pred p;\n"
+			"mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+			"selp.u32 %0, 1, 0, p;\n"
+			"}\n" : "=r"(ok) : "r"(stm_smem(bar)), "r"(parity) : "memory");
+		if (ok) return true;
+	}
+	return false;
 }
 __device__ __forceinline__ void stm_tma_load(void* smem_dst, const CUtensorMap* tm, int c0, int c1, u64* bar) {
 	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -143,7 +146,7 @@ clo_scan_tma(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ 
 		const bool red = r >= 0 && t_red < num_tiles;
 		if (red) {
 			const int slot = r % S;
-			stm_mbar_wait(&s_full[slot], (u32) (r / S) & 1u);
+			if (!stm_mbar_wait(&s_full[slot], (u32) (r / S) & 1u) && lane == 0) atomicExch(err_flag, 1);
 			unsigned char* tile = ring + (size_t) slot * TILE_BYTES;
 			IntraT part[4];
 #pragma unroll
