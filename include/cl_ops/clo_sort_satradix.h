@@ -10,7 +10,19 @@
  *   1  clo_radix_scan_bins     exclusive scan of the bins (global digit offsets)
  *   2  clo_radix_onesweep_v6   rank + decoupled prefix + staged scatter, once per 8-bit digit
  * The names are the CUDA kernels' real names (clo_sort_get_kernel_name returns them) and
- * clo_sort_get_localmem_usage returns their real shared-memory sizes.
+ * clo_sort_get_localmem_usage returns their real shared-memory sizes.  Small helpers run beside
+ * them: clo_radix_chain_fixup (one conditional copy after the last pass: a pass whose digit is
+ * the same for every key moves nothing), clo_radix_typed_flip (typed_order), and for a get_key
+ * string outside the menu the run-time compiled clo_jit_extract_keys + clo_radix_gather.
+ *
+ * Options (clo_sort_new's `options` string, comma separated key=value):
+ *   radix=R        the reference's digit width option (clo_sort_satradix.c:352,385-392): a power
+ *                  of two; only decides how many bits of the key are sorted, as there
+ *                  (total_digits = elem_bits / log2 R); the passes here are always 8 bits wide.
+ *   scan=blelloch, scan...   accepted as in the reference (it forwards them to its scanner).
+ *   typed_order=1  NOT in the reference, opt-in: signed integers and floats sort by VALUE.  The
+ *                  default is the reference's order: raw key bits ascending (negative integers
+ *                  after positive ones), float keys rejected (`key >> b` does not compile there).
  */
 #ifndef CLO_B200_SORT_SATRADIX_H
 #define CLO_B200_SORT_SATRADIX_H
