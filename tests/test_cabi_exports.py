@@ -113,3 +113,18 @@ def test_per_algorithm_headers_compile_on_their_own(header, tmp_path):
     r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
                         "-I", os.path.join(ROOT, "include", "compat"), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_dist_rng_partition_is_a_partition():
+    """clo_dist_rng_partition (pure host arithmetic, no device needed): contiguous, disjoint,
+    complete, sizes differ by at most one -- for every world size the library supports."""
+    import ctypes
+    import cl_ops_b200 as clo
+    for total in (0, 1, 7, 1 << 22, (1 << 32) + 12345):
+        for world in range(1, 17):
+            spans = [clo.CloDist.rng_partition(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0
+            assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            assert spans[-1][0] + spans[-1][1] == total
+            sizes = [c for _, c in spans]
+            assert max(sizes) - min(sizes) <= 1
